@@ -1,0 +1,139 @@
+// device_index.cuh -- device-side view of the uploaded blob and the rank primitives.
+// The blob sits in HBM byte-for-byte; these are typed pointers into it (the device twin of the
+// reference's CountArrayView / SuffixArrayView / BwmView, components/*.rs).
+// Citations are relative to the reference's sview-fmindex/src/.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace svfm {
+
+template <class P>
+struct DevIndex {
+    // CountArrayView (components/count_array.rs:21-29)
+    const P* count_array;             // P[S+1]
+    const uint64_t* kmer_multiplier;  // usize[k]
+    const P* kmer_count_table;        // P[(S+1)^k]
+    // SuffixArrayView (components/suffix_array/mod.rs:21-26)
+    const P* suffix_array;
+    // BwmView (components/bwm/mod.rs:19-26)
+    const P* rank_checkpoints;        // row-major [block][symbol], row stride = symbol_count
+    const void* blocks;               // BlockN<V>[blocks_len]
+    const uint8_t* table;             // EncodingTable bytes, or NULL for PassThrough
+    P sentinel_index;
+    uint32_t symbol_count;            // S (row stride; bwm/mod.rs:158)
+    uint32_t kmer_size;               // k
+    uint32_t sampling_ratio;          // r
+    uint32_t ratio_mask;              // r-1 if r is a power of two, else 0xffffffff
+    uint32_t ratio_shift;             // log2(r) if power of two
+    uint64_t kmer_top_multiplier;     // (S+1)^(k-1) = kmer_multiplier[0]
+};
+
+// ---- loads --------------------------------------------------------------------------------------
+// Random gathers with no reuse inside a CTA: read-only path, do not allocate in L1 so that the small
+// tables (encoding table, count array, kLTS) stay resident.
+__device__ __forceinline__ uint32_t ld_gather_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+template <class P> __device__ __forceinline__ P ld_gather(const P* p);
+template <> __device__ __forceinline__ uint32_t ld_gather<uint32_t>(const uint32_t* p) { return ld_gather_u32(p); }
+template <> __device__ __forceinline__ uint64_t ld_gather<uint64_t>(const uint64_t* p) { return ld_gather_u64(p); }
+
+// ---- one occ block held in registers ---------------------------------------------------------------
+// BlockN<V>([V; N]) (blocks/block2.rs:7 .. block6.rs:7).  Symbol j of the block is bit VBITS-1-j of
+// every plane (vectorize shifts left once per symbol, block3.rs:20-35).  A plane is kept as WORDS
+// machine words ordered from the most significant (first symbols) to the least:
+//   u32  -> 1 x 32-bit word      u64 -> 1 x 64-bit word
+//   u128 -> 2 x 64-bit words; little-endian in memory, so word 0 (symbols 0..63) is at byte offset 8.
+template <int VBITS> struct VecTraits;
+template <> struct VecTraits<32>  { using W = uint32_t; static constexpr int WORDS = 1; static constexpr int WBITS = 32; static constexpr int LOG2 = 5; };
+template <> struct VecTraits<64>  { using W = uint64_t; static constexpr int WORDS = 1; static constexpr int WBITS = 64; static constexpr int LOG2 = 6; };
+template <> struct VecTraits<128> { using W = uint64_t; static constexpr int WORDS = 2; static constexpr int WBITS = 64; static constexpr int LOG2 = 7; };
+
+__device__ __forceinline__ int popc_w(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popc_w(uint64_t x) { return __popcll(x); }
+
+template <int NPL, int VBITS>
+struct Block {
+    using T = VecTraits<VBITS>;
+    using W = typename T::W;
+    W w[NPL][T::WORDS];
+
+    __device__ __forceinline__ void load(const void* blocks, uint64_t q) {
+        const W* base = reinterpret_cast<const W*>(blocks) + q * (uint64_t)(NPL * T::WORDS);
+#pragma unroll
+        for (int v = 0; v < NPL; v++) {
+            if (T::WORDS == 1) {
+                w[v][0] = ld_gather<W>(base + v);
+            } else {
+                w[v][T::WORDS - 1] = ld_gather<W>(base + v * 2 + 0);  // low half  = symbols 64..127
+                w[v][0] = ld_gather<W>(base + v * 2 + 1);              // high half = symbols 0..63
+            }
+        }
+    }
+
+    // AND over planes of (bit v of symidx ? plane : !plane): the `match symidx` of get_remain_count_of
+    // (block2.rs:39-44, block3.rs:43-52, block4.rs:47-64, block5.rs:51-84, block6.rs:55-120).
+    __device__ __forceinline__ void match_mask(uint32_t symidx, W (&m)[T::WORDS]) const {
+#pragma unroll
+        for (int k = 0; k < T::WORDS; k++) m[k] = ~(W)0;
+#pragma unroll
+        for (int v = 0; v < NPL; v++) {
+            const W flip = ((symidx >> v) & 1u) ? (W)0 : ~(W)0;
+#pragma unroll
+            for (int k = 0; k < T::WORDS; k++) m[k] &= (w[v][k] ^ flip);
+        }
+    }
+
+    // popcount of the first `rem` symbols of a match mask; rem in [0, VBITS) (0 -> 0).
+    __device__ __forceinline__ static uint32_t prefix_count(const W (&m)[T::WORDS], uint32_t rem) {
+        if (T::WORDS == 1) {
+            // count_bits >>= BLOCK_LEN - rem; count_ones()   (block3.rs:53-54); rem == 0 never shifts
+            return rem ? (uint32_t)popc_w((W)(m[0] >> (T::WBITS - rem))) : 0u;
+        } else {
+            uint32_t r0 = rem < 64u ? rem : 64u;  // symbols taken from word 0
+            uint32_t r1 = rem - r0;               // symbols taken from word 1
+            uint32_t c = r0 ? (uint32_t)popc_w((W)(m[0] >> (64u - r0))) : 0u;
+            c += r1 ? (uint32_t)popc_w((W)(m[1] >> (64u - r1))) : 0u;
+            return c;
+        }
+    }
+
+    // get_remain_count_of(rem, symidx) (block3.rs:42-55)
+    __device__ __forceinline__ uint32_t remain_count(uint32_t rem, uint32_t symidx) const {
+        W m[T::WORDS];
+        match_mask(symidx, m);
+        return prefix_count(m, rem);
+    }
+
+    // get_symidx_of(rem) (block3.rs:57-63): bit (VBITS-1-rem) of every plane, rem in [0, VBITS)
+    __device__ __forceinline__ uint32_t symidx_of(uint32_t rem) const {
+        uint32_t s = 0;
+        const int k = (T::WORDS == 1) ? 0 : (int)(rem >> 6);
+        const uint32_t sh = T::WBITS - 1 - (rem & (T::WBITS - 1));
+#pragma unroll
+        for (int v = 0; v < NPL; v++) {
+            W word = (T::WORDS == 1) ? w[v][0] : (k ? w[v][T::WORDS - 1] : w[v][0]);
+            s |= (uint32_t)((word >> sh) & 1u) << v;
+        }
+        return s;
+    }
+};
+
+// BwmView::get_next_rank (components/bwm/mod.rs:197-215) split in two so that the caller can issue
+// the loads of several ranks before consuming any of them.
+template <class P, int VBITS>
+__device__ __forceinline__ void rank_addr(const DevIndex<P>& ix, P pos, uint64_t& q, uint32_t& rem) {
+    if (pos < ix.sentinel_index) pos += 1;                  // bwm/mod.rs:202-204
+    q = (uint64_t)pos >> VecTraits<VBITS>::LOG2;            // div_rem_with_u32(BLOCK_LEN), text_length.rs:78
+    rem = (uint32_t)pos & (uint32_t)(VBITS - 1);
+}
+
+}  // namespace svfm

@@ -1,0 +1,612 @@
+// svfm_api.cu -- C ABI (include/svfm.h) of the B200-native batched FM-index search engine.
+// Index handle, sessions (stream + scratch arena), host/device batch entry points.
+// Citations are relative to the reference's sview-fmindex/src/.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "blob_layout.h"
+#include "common.cuh"
+#include "search_kernels.cuh"
+
+namespace svfm {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+// ---------------------------------------------------------------------------------------------
+// index handle
+// ---------------------------------------------------------------------------------------------
+}  // namespace svfm
+
+struct svfm_index {
+    svfm_type type;
+    svfm::Layout L;
+    int device = 0;
+    uint8_t* d_alloc = nullptr;  // cudaMalloc base
+    uint8_t* d_blob = nullptr;   // d_alloc + pad: the blob, byte-for-byte
+    uint64_t blob_len = 0;
+    uint64_t text_len = 0;
+    uint64_t sentinel_index = 0;
+    std::mutex pool_mu;
+    std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
+};
+
+struct svfm_session {
+    svfm_index* ix = nullptr;
+    cudaStream_t stream = nullptr;
+    svfm::DeviceBuffer pats, offs, sp, cnt, out_offs, positions, positions_alt, cub_temp;
+    int* d_err = nullptr;
+    uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
+};
+
+namespace svfm {
+
+template <class P>
+static DevIndex<P> make_dev_index(const svfm_index* ix) {
+    const Layout& L = ix->L;
+    DevIndex<P> d;
+    d.count_array = reinterpret_cast<const P*>(ix->d_blob + L.off_count_array);
+    d.kmer_multiplier = reinterpret_cast<const uint64_t*>(ix->d_blob + L.off_kmer_multiplier);
+    d.kmer_count_table = reinterpret_cast<const P*>(ix->d_blob + L.off_kmer_count_table);
+    d.suffix_array = reinterpret_cast<const P*>(ix->d_blob + L.off_suffix_array);
+    d.rank_checkpoints = reinterpret_cast<const P*>(ix->d_blob + L.off_rank_checkpoints);
+    d.blocks = ix->d_blob + L.off_blocks;
+    d.table = ix->type.encoder ? ix->d_blob + L.off_encoder : nullptr;
+    d.sentinel_index = (P)ix->sentinel_index;
+    d.symbol_count = L.bwm_symbol_count;
+    d.kmer_size = L.kmer_size;
+    d.sampling_ratio = L.sampling_ratio;
+    const uint32_t r = L.sampling_ratio;
+    if ((r & (r - 1)) == 0) {
+        d.ratio_mask = r - 1;
+        d.ratio_shift = 0;
+        while ((1u << d.ratio_shift) < r) d.ratio_shift++;
+    } else {
+        d.ratio_mask = 0xffffffffu;
+        d.ratio_shift = 0;
+    }
+    d.kmer_top_multiplier = 0;
+    return d;
+}
+
+static int finish_load(svfm_index* ix) {
+    // text length is not stored in a header: it equals count_array[S] (count_array.rs:117,125)
+    const Layout& L = ix->L;
+    uint64_t v = 0;
+    const uint64_t P = ix->type.pos_bits / 8;
+    SVFM_CUDA(cudaMemcpy(&v, ix->d_blob + L.off_count_array + (uint64_t)(L.count_array_len - 1) * P, P, cudaMemcpyDeviceToHost));
+    ix->text_len = v;
+    v = 0;
+    SVFM_CUDA(cudaMemcpy(&v, ix->d_blob + L.off_sentinel_index, P, cudaMemcpyDeviceToHost));
+    ix->sentinel_index = v;
+    // the device kernels index blocks[pos / BLOCK_LEN] for pos <= text_len: make sure the header agrees
+    if (ix->text_len / ix->type.vec_bits + 1 != L.blocks_len || ix->sentinel_index > ix->text_len ||
+        ix->sentinel_index == 0)
+        return SVFM_ERR_INVALID_FORMAT;
+    const uint64_t r = L.sampling_ratio;
+    if (ix->text_len / r + (ix->text_len % r ? 1 : 0) != L.suffix_array_len) return SVFM_ERR_INVALID_FORMAT;
+    return SVFM_OK;
+}
+
+static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int device, bool src_on_device,
+                       svfm_index** out, uint64_t err_detail[2]) {
+    if (!out) return SVFM_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!type_ok(t)) return SVFM_ERR_BAD_TYPE;
+    if (!blob) return SVFM_ERR_BAD_ARG;
+    if (src_on_device) SVFM_CUDA(cudaSetDevice(device));
+    Layout L;
+    int rc = parse_blob(
+        [&](uint8_t* dst, uint64_t off, uint64_t n) {
+            if (src_on_device) return cudaMemcpy(dst, blob + off, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+            std::memcpy(dst, blob + off, n);
+            return true;
+        },
+        blob_len, t, L, err_detail);
+    if (rc) return rc;
+    SVFM_CUDA(cudaSetDevice(device));
+    svfm_index* ix = new svfm_index();
+    ix->type = t;
+    ix->L = L;
+    ix->device = device;
+    ix->blob_len = blob_len;
+    // Shift the device copy so that the blocks section starts on a 32-byte boundary (sections are only
+    // 8/16-byte aligned inside the blob): 16- and 32-byte blocks then never straddle a 32 B sector.
+    const uint64_t pad = (32 - (L.off_blocks % 32)) % 32;
+    cudaError_t e = cudaMalloc(&ix->d_alloc, blob_len + pad + 64);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaMalloc(blob): ") + cudaGetErrorString(e);
+        delete ix;
+        return e == cudaErrorMemoryAllocation ? SVFM_ERR_NOMEM : SVFM_ERR_CUDA;
+    }
+    ix->d_blob = ix->d_alloc + pad;
+    e = cudaMemcpy(ix->d_blob, blob, blob_len, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaMemcpy(blob): ") + cudaGetErrorString(e);
+        cudaFree(ix->d_alloc);
+        delete ix;
+        return SVFM_ERR_CUDA;
+    }
+    rc = finish_load(ix);
+    if (rc) {
+        cudaFree(ix->d_alloc);
+        delete ix;
+        return rc;
+    }
+    *out = ix;
+    return SVFM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sessions
+// ---------------------------------------------------------------------------------------------
+static int session_new(svfm_index* ix, svfm_session** out) {
+    SVFM_CUDA(cudaSetDevice(ix->device));
+    svfm_session* s = new svfm_session();
+    s->ix = ix;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 4 * sizeof(uint64_t), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("session_new: ") + cudaGetErrorString(e);
+        delete s;
+        return SVFM_ERR_CUDA;
+    }
+    *out = s;
+    return SVFM_OK;
+}
+
+static void session_delete(svfm_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->ix->device);
+    if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    if (s->d_err) cudaFree(s->d_err);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    delete s;
+}
+
+struct SessionLease {
+    svfm_index* ix;
+    svfm_session* s = nullptr;
+    explicit SessionLease(svfm_index* i) : ix(i) {}
+    int acquire() {
+        {
+            std::lock_guard<std::mutex> g(ix->pool_mu);
+            if (!ix->pool.empty()) { s = ix->pool.back(); ix->pool.pop_back(); }
+        }
+        if (s) return cudaSetDevice(ix->device) == cudaSuccess ? SVFM_OK : SVFM_ERR_CUDA;
+        return session_new(ix, &s);
+    }
+    ~SessionLease() {
+        if (s) { std::lock_guard<std::mutex> g(ix->pool_mu); ix->pool.push_back(s); }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch over the 30 (P, BlockN, Vector) instantiations
+// ---------------------------------------------------------------------------------------------
+static int grid_for(uint64_t work_items, int threads, int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sms * 8;  // a whole number of waves of resident CTAs; grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+template <class P, int NPL, int VBITS>
+static int run_search(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) {
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    const int grid = grid_for(pb.n, SEARCH_THREADS, s->ix->device);
+    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, (P*)d_sp, (P*)d_cnt, s->d_err);
+    g_launches++;
+    SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+
+template <class P>
+struct WidenCounts {
+    const P* cnt;
+    uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)cnt[i] : 0ull; }
+};
+
+template <class P, int NPL, int VBITS>
+static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) {
+    // out_offs[0..n] = exclusive prefix sums of the counts, widened to u64 (out_offs[n] = total)
+    WidenCounts<P> f{(const P*)d_cnt, n};
+    auto in = thrust::make_transform_iterator(thrust::counting_iterator<uint64_t>(0), f);
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_out_offs, n + 1, s->stream));
+    int rc = s->cub_temp.reserve(temp);
+    if (rc) return rc;
+    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_temp.ptr, temp, in, d_out_offs, n + 1, s->stream));
+    g_launches += 2;
+    return SVFM_OK;
+}
+
+template <class P, int NPL, int VBITS>
+static int run_locate(svfm_session* s, uint64_t n, const void* d_sp, const uint64_t* d_out_offs, uint64_t total,
+                      void* d_positions) {
+    if (total == 0) return SVFM_OK;
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    const uint64_t blocks = (total + LOCATE_THREADS - 1) / LOCATE_THREADS;
+    if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
+    locate_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
+        dix, (const P*)d_sp, d_out_offs, n, total, (P*)d_positions);
+    g_launches++;
+    SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+
+template <class P, int NPL, int VBITS>
+static int run_sort_segments(svfm_session* s, uint64_t n, const uint64_t* d_out_offs, uint64_t total,
+                             void** d_positions_inout) {
+    // SVFM_SORTED: ascending positions inside every pattern's segment (the reference returns SA-row order;
+    // its tests sort before comparing, get_accurate_result/mod.rs:53-56).
+    if (total == 0 || n == 0) return SVFM_OK;
+    if (total > 0x7fffffffull || n > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
+    int rc = s->positions_alt.reserve(total * sizeof(P));
+    if (rc) return rc;
+    cub::DoubleBuffer<P> keys((P*)*d_positions_inout, (P*)s->positions_alt.ptr);
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, temp, keys, (int)total, (int)n, d_out_offs, d_out_offs + 1, s->stream));
+    rc = s->cub_temp.reserve(temp);
+    if (rc) return rc;
+    SVFM_CUDA(cub::DeviceSegmentedSort::SortKeys(s->cub_temp.ptr, temp, keys, (int)total, (int)n, d_out_offs, d_out_offs + 1, s->stream));
+    g_launches += 3;
+    if (keys.Current() != (P*)*d_positions_inout) {
+        std::swap(s->positions, s->positions_alt);
+        *d_positions_inout = s->positions.ptr;
+    }
+    return SVFM_OK;
+}
+
+#define SVFM_DISPATCH_N(P, VB, FN, ...)                                     \
+    switch (t.planes) {                                                     \
+        case 2: return FN<P, 2, VB>(__VA_ARGS__);                           \
+        case 3: return FN<P, 3, VB>(__VA_ARGS__);                           \
+        case 4: return FN<P, 4, VB>(__VA_ARGS__);                           \
+        case 5: return FN<P, 5, VB>(__VA_ARGS__);                           \
+        case 6: return FN<P, 6, VB>(__VA_ARGS__);                           \
+        default: return SVFM_ERR_BAD_TYPE;                                  \
+    }
+#define SVFM_DISPATCH_V(P, FN, ...)                                         \
+    switch (t.vec_bits) {                                                   \
+        case 32: SVFM_DISPATCH_N(P, 32, FN, __VA_ARGS__)                    \
+        case 64: SVFM_DISPATCH_N(P, 64, FN, __VA_ARGS__)                    \
+        case 128: SVFM_DISPATCH_N(P, 128, FN, __VA_ARGS__)                  \
+        default: return SVFM_ERR_BAD_TYPE;                                  \
+    }
+#define SVFM_DISPATCH(FN, ...)                                              \
+    do {                                                                    \
+        const svfm_type& t = s->ix->type;                                   \
+        if (t.pos_bits == 32) { SVFM_DISPATCH_V(uint32_t, FN, __VA_ARGS__) } \
+        else { SVFM_DISPATCH_V(uint64_t, FN, __VA_ARGS__) }                 \
+    } while (0)
+
+static int dispatch_search(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) { SVFM_DISPATCH(run_search, s, pb, d_sp, d_cnt); }
+static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
+static int dispatch_locate(svfm_session* s, uint64_t n, const void* d_sp, const uint64_t* d_out_offs, uint64_t total, void* d_positions) { SVFM_DISPATCH(run_locate, s, n, d_sp, d_out_offs, total, d_positions); }
+static int dispatch_sort(svfm_session* s, uint64_t n, const uint64_t* d_out_offs, uint64_t total, void** d_positions) { SVFM_DISPATCH(run_sort_segments, s, n, d_out_offs, total, d_positions); }
+
+static int err_from_bits(int bits) {
+    if (bits & ERRBIT_EMPTY_PATTERN) return SVFM_ERR_EMPTY_PATTERN;
+    if (bits & ERRBIT_BAD_SYMBOL) return SVFM_ERR_BAD_SYMBOL;
+    return SVFM_OK;
+}
+
+// Device-resident count: search kernel only.  Leaves the error bits in s->d_err (checked by the caller).
+static int count_device(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) {
+    SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
+    if (pb.n == 0) return SVFM_OK;
+    return dispatch_search(s, pb, d_sp, d_cnt);
+}
+
+// Device-resident locate pipeline: search -> scan -> (sync for the total) -> LF-walk -> optional sort.
+static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags, uint64_t* d_out_offs,
+                         void** d_positions, uint64_t* total_out) {
+    const uint64_t P = s->ix->type.pos_bits / 8;
+    int rc;
+    if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
+    if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
+    if ((rc = count_device(s, pb, s->sp.ptr, s->cnt.ptr))) return rc;
+    if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, d_out_offs))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], d_out_offs + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    if ((rc = err_from_bits((int)(s->h_pinned[1] & 0xffffffffu)))) return rc;
+    const uint64_t total = s->h_pinned[0];
+    *total_out = total;
+    if ((rc = s->positions.reserve((total + 1) * P))) return rc;
+    *d_positions = s->positions.ptr;
+    if ((rc = dispatch_locate(s, pb.n, s->sp.ptr, d_out_offs, total, s->positions.ptr))) return rc;
+    if (flags & SVFM_SORTED) {
+        if ((rc = dispatch_sort(s, pb.n, d_out_offs, total, d_positions))) return rc;
+    }
+    return SVFM_OK;
+}
+
+// Host-side validation shared by the host-buffer entry points.
+static int check_host_patterns(const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                               uint64_t* total_bytes) {
+    if (n == 0) { *total_bytes = 0; return SVFM_OK; }
+    if (!pats) return SVFM_ERR_BAD_ARG;
+    if (!offs) {
+        if (fixed_len == 0) return SVFM_ERR_EMPTY_PATTERN;
+        *total_bytes = n * (uint64_t)fixed_len;
+        return SVFM_OK;
+    }
+    for (uint64_t i = 0; i < n; i++) {
+        if (offs[i + 1] < offs[i]) return SVFM_ERR_BAD_ARG;
+        if (offs[i + 1] == offs[i]) return SVFM_ERR_EMPTY_PATTERN;
+    }
+    *total_bytes = offs[n];
+    return SVFM_OK;
+}
+
+static int upload_patterns(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                           uint32_t flags, PatternBatch& pb) {
+    uint64_t bytes = 0;
+    int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
+    if (rc) return rc;
+    pb.n = n;
+    pb.fixed_len = fixed_len;
+    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.pats = nullptr;
+    pb.offs = nullptr;
+    if (n == 0) return SVFM_OK;
+    const uint64_t base = offs ? offs[0] : 0;
+    if ((rc = s->pats.reserve(bytes - base + 16))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + base, bytes - base, cudaMemcpyHostToDevice, s->stream));
+    pb.pats = (const uint8_t*)s->pats.ptr - base;  // offsets stay absolute
+    if (offs) {
+        if ((rc = s->offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
+        SVFM_CUDA(cudaMemcpyAsync(s->offs.ptr, offs, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        pb.offs = (const uint64_t*)s->offs.ptr;
+    }
+    return SVFM_OK;
+}
+
+}  // namespace svfm
+
+using namespace svfm;
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int svfm_load(const uint8_t* blob, size_t blob_len, svfm_type t, int device, svfm_index** out, uint64_t err_detail[2]) {
+    return load_common(blob, blob_len, t, device, false, out, err_detail);
+}
+
+int svfm_load_device(const uint8_t* d_blob, size_t blob_len, svfm_type t, int device, svfm_index** out, uint64_t err_detail[2]) {
+    return load_common(d_blob, blob_len, t, device, true, out, err_detail);
+}
+
+int svfm_check_blob(const uint8_t* blob, size_t blob_len, svfm_type t, svfm_info* out, uint64_t err_detail[2]) {
+    if (!blob) return SVFM_ERR_BAD_ARG;
+    Layout L;
+    int rc = parse_blob([&](uint8_t* dst, uint64_t off, uint64_t n) { std::memcpy(dst, blob + off, n); return true; },
+                        blob_len, t, L, err_detail);
+    if (rc) return rc;
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->type = t;
+        out->device = -1;
+        out->symbol_count = L.symbol_count;
+        out->kmer_size = L.kmer_size;
+        out->sampling_ratio = L.sampling_ratio;
+        const uint64_t P = t.pos_bits / 8;
+        std::memcpy(&out->text_len, blob + L.off_count_array + (uint64_t)(L.count_array_len - 1) * P, P);
+        std::memcpy(&out->sentinel_index, blob + L.off_sentinel_index, P);
+        out->suffix_array_len = L.suffix_array_len;
+        out->blocks_len = L.blocks_len;
+        out->blob_len = blob_len;
+        out->header_size = L.header_size;
+        out->off_suffix_array = L.off_suffix_array;
+        out->off_rank_checkpoints = L.off_rank_checkpoints;
+        out->off_blocks = L.off_blocks;
+    }
+    return SVFM_OK;
+}
+
+void svfm_free(svfm_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    for (svfm_session* s : ix->pool) session_delete(s);
+    ix->pool.clear();
+    if (ix->d_alloc) cudaFree(ix->d_alloc);
+    delete ix;
+}
+
+int svfm_index_info(const svfm_index* ix, svfm_info* out) {
+    if (!ix || !out) return SVFM_ERR_BAD_ARG;
+    std::memset(out, 0, sizeof(*out));
+    out->type = ix->type;
+    out->device = ix->device;
+    out->symbol_count = ix->L.symbol_count;
+    out->kmer_size = ix->L.kmer_size;
+    out->sampling_ratio = ix->L.sampling_ratio;
+    out->text_len = ix->text_len;
+    out->suffix_array_len = ix->L.suffix_array_len;
+    out->blocks_len = ix->L.blocks_len;
+    out->sentinel_index = ix->sentinel_index;
+    out->blob_len = ix->blob_len;
+    out->header_size = ix->L.header_size;
+    out->off_suffix_array = ix->L.off_suffix_array;
+    out->off_rank_checkpoints = ix->L.off_rank_checkpoints;
+    out->off_blocks = ix->L.off_blocks;
+    return SVFM_OK;
+}
+
+int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                     uint32_t flags, void* counts_out) {
+    if (!ix || (n && !counts_out)) return SVFM_ERR_BAD_ARG;
+    uint64_t bytes = 0;
+    int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
+    if (rc) return rc;
+    if (n == 0) return SVFM_OK;
+    SessionLease lease(ix);
+    if ((rc = lease.acquire())) return rc;
+    svfm_session* s = lease.s;
+    const uint64_t P = ix->type.pos_bits / 8;
+    PatternBatch pb;
+    if ((rc = upload_patterns(s, pats, offs, n, fixed_len, flags, pb))) return rc;
+    if ((rc = s->cnt.reserve(n * P))) return rc;
+    if ((rc = count_device(s, pb, nullptr, s->cnt.ptr))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(counts_out, s->cnt.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
+}
+
+static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                       uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, void** alloc_out,
+                       uint64_t* total_out) {
+    if (!ix || !out_offs || !total_out) return SVFM_ERR_BAD_ARG;
+    *total_out = 0;
+    if (alloc_out) *alloc_out = nullptr;
+    uint64_t bytes = 0;
+    int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
+    if (rc) return rc;
+    out_offs[0] = 0;
+    if (n == 0) return SVFM_OK;
+    SessionLease lease(ix);
+    if ((rc = lease.acquire())) return rc;
+    svfm_session* s = lease.s;
+    const uint64_t P = ix->type.pos_bits / 8;
+    PatternBatch pb;
+    if ((rc = upload_patterns(s, pats, offs, n, fixed_len, flags, pb))) return rc;
+    if ((rc = s->out_offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
+    void* d_positions = nullptr;
+    uint64_t total = 0;
+    if ((rc = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return rc;
+    *total_out = total;
+    SVFM_CUDA(cudaMemcpyAsync(out_offs, s->out_offs.ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    void* dst = positions;
+    if (alloc_out) {
+        if (total) {
+            cudaError_t e = cudaHostAlloc(&dst, total * P, cudaHostAllocDefault);
+            if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); g_last_error = cudaGetErrorString(e); return SVFM_ERR_NOMEM; }
+        } else dst = nullptr;
+        *alloc_out = dst;
+    } else if (total > capacity) {
+        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        return SVFM_ERR_CAPACITY;
+    }
+    if (total) SVFM_CUDA(cudaMemcpyAsync(dst, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    return SVFM_OK;
+}
+
+int svfm_locate_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                      uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, uint64_t* total) {
+    if (capacity && !positions) return SVFM_ERR_BAD_ARG;
+    return locate_host(ix, pats, offs, n, fixed_len, flags, out_offs, positions, capacity, nullptr, total);
+}
+
+int svfm_locate_batch_alloc(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                            uint32_t flags, uint64_t* out_offs, void** positions, uint64_t* total) {
+    if (!positions) return SVFM_ERR_BAD_ARG;
+    return locate_host(ix, pats, offs, n, fixed_len, flags, out_offs, nullptr, 0, positions, total);
+}
+
+void svfm_free_positions(void* positions) {
+    if (positions) cudaFreeHost(positions);
+}
+
+int svfm_count(svfm_index* ix, const uint8_t* pattern, uint64_t len, uint32_t flags, uint64_t* count) {
+    if (!ix || !count) return SVFM_ERR_BAD_ARG;
+    if (len == 0) return SVFM_ERR_EMPTY_PATTERN;
+    if (len > 0xffffffffull) return SVFM_ERR_BAD_ARG;
+    uint64_t c = 0;  // P-sized write into a zeroed u64 (little-endian)
+    int rc = svfm_count_batch(ix, pattern, nullptr, 1, (uint32_t)len, flags, &c);
+    if (rc) return rc;
+    *count = c;
+    return SVFM_OK;
+}
+
+int svfm_locate(svfm_index* ix, const uint8_t* pattern, uint64_t len, uint32_t flags, void* positions,
+                uint64_t capacity, uint64_t* total) {
+    if (!ix || !total) return SVFM_ERR_BAD_ARG;
+    if (len == 0) return SVFM_ERR_EMPTY_PATTERN;
+    if (len > 0xffffffffull) return SVFM_ERR_BAD_ARG;
+    uint64_t offs2[2];
+    return svfm_locate_batch(ix, pattern, nullptr, 1, (uint32_t)len, flags, offs2, positions, capacity, total);
+}
+
+int svfm_session_create(svfm_index* ix, svfm_session** out) {
+    if (!ix || !out) return SVFM_ERR_BAD_ARG;
+    return session_new(ix, out);
+}
+
+void svfm_session_destroy(svfm_session* s) { session_delete(s); }
+
+int svfm_session_sync(svfm_session* s) {
+    if (!s) return SVFM_ERR_BAD_ARG;
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    // status of the device-side pattern checks of the last batch enqueued on this session
+    const int rc = err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
+    s->h_pinned[1] = 0;
+    return rc;
+}
+
+void* svfm_session_stream(svfm_session* s) { return s ? (void*)s->stream : nullptr; }
+
+int svfm_count_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
+                            uint32_t fixed_len, uint32_t flags, void* d_counts_out) {
+    if (!s || (n && (!d_pats || !d_counts_out))) return SVFM_ERR_BAD_ARG;
+    if (!d_offs && fixed_len == 0 && n) return SVFM_ERR_EMPTY_PATTERN;
+    SVFM_CUDA(cudaSetDevice(s->ix->device));
+    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
+    int rc = count_device(s, pb, nullptr, d_counts_out);
+    if (rc) return rc;
+    // the error word is read back asynchronously; svfm_session_sync + the next call report it
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    return SVFM_OK;
+}
+
+int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
+                             uint32_t fixed_len, uint32_t flags, uint64_t* d_out_offs, void** d_positions,
+                             uint64_t* total) {
+    if (!s || !d_out_offs || !d_positions || !total || (n && !d_pats)) return SVFM_ERR_BAD_ARG;
+    if (!d_offs && fixed_len == 0 && n) return SVFM_ERR_EMPTY_PATTERN;
+    SVFM_CUDA(cudaSetDevice(s->ix->device));
+    *total = 0;
+    *d_positions = nullptr;
+    if (n == 0) {
+        SVFM_CUDA(cudaMemsetAsync(d_out_offs, 0, sizeof(uint64_t), s->stream));
+        return SVFM_OK;
+    }
+    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
+    return locate_device(s, pb, flags, d_out_offs, d_positions, total);
+}
+
+void* svfm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void svfm_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+const char* svfm_last_error(void) { return g_last_error.c_str(); }
+uint64_t svfm_launch_count(void) { return g_launches.load(); }
+const char* svfm_version(void) { return "sview-fmindex-b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI, sview_fmindex_b200/libsvfm.so) against the CPU
+oracle on identical blobs and patterns.  Bit-exact: counts, CSR offsets and positions in the reference's
+SA-row order (locate/mod.rs:19).  Mirrors the reference's tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ALL_TYPES, brute_force_locate, gen_rand_chr_list, gen_rand_pattern, gen_rand_text
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "readme_example.json")
+
+
+@pytest.fixture(scope="module")
+def fm():
+    import sview_fmindex_b200 as fm
+    from sview_fmindex_b200 import _ffi
+    _ffi.lib()
+    return fm
+
+
+def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
+    table, sc = po.encoding_table(symbols, with_wildcard)
+    if passthrough:
+        t = po.IndexType(p, n, v, False)
+        blob = po.build_blob(t, table[np.frombuffer(bytes(text), dtype=np.uint8)], sc, None, k, r)
+    else:
+        t = po.IndexType(p, n, v, True)
+        blob = po.build_blob(t, text, sc, table, k, r)
+    ora = po.OracleFmIndex.load(blob, t)
+    gpu = fm.FmIndex.load(blob, fm.IndexType(p, n, v, not passthrough))
+    return ora, gpu, table, sc
+
+
+def _check_batch(ora, gpu, patterns, reversed_=False):
+    counts = gpu.count_batch(patterns, reversed_=reversed_)
+    offs, pos = gpu.locate_batch(patterns, reversed_=reversed_)
+    offs_s, pos_s = gpu.locate_batch(patterns, sorted_=True, reversed_=reversed_)
+    assert np.array_equal(offs, offs_s)
+    for i, pat in enumerate(patterns):
+        pat = bytes(pat)
+        exp = ora.locate_rev_iter(pat) if reversed_ else ora.locate(pat)
+        assert int(counts[i]) == len(exp), (i, pat)
+        got = pos[int(offs[i]):int(offs[i + 1])].astype(np.uint64)
+        assert np.array_equal(got, exp), (i, pat)  # SA-row order, bit-exact
+        got_s = pos_s[int(offs[i]):int(offs[i + 1])].astype(np.uint64)
+        assert np.array_equal(got_s, np.sort(exp)), (i, pat)
+
+
+def test_readme_golden(oracle, fm):
+    g = json.load(open(GOLDEN))
+    ora, gpu, _, sc = _pair(oracle, fm, g["text"].encode(), [s.encode() for s in g["symbols"]], 32, 2, 64, 1, 1)
+    assert sc == 4
+    for q in g["queries"]:
+        pat = q["pattern"].encode()
+        assert gpu.count(pat) == q["count"]
+        assert sorted(int(x) for x in gpu.locate(pat)) == q["locate_sorted"]
+        assert gpu.count_rev_iter(pat[::-1]) == q["count"]
+        assert sorted(int(x) for x in gpu.locate_rev_iter(pat[::-1])) == q["locate_sorted"]
+        buf = [7]
+        gpu.locate_to_buffer(pat, buf)  # appends without clearing
+        assert buf[0] == 7 and sorted(buf[1:]) == q["locate_sorted"]
+    info = gpu.info()
+    assert info.text_len == 31 and info.sentinel_index == g["sentinel_index"] and info.header_size == 328
+
+
+@pytest.mark.parametrize("chr_count", [3, 4, 5, 7, 8, 9, 15, 16, 17, 33, 64])
+def test_results_are_accurate(oracle, fm, chr_count):
+    """get_accurate_result/mod.rs:61-142 on the GPU: every (P, Block, Vector) that can hold the alphabet,
+    ltks=3, sasr=2; answers = brute force AND the oracle (bit-exact, SA-row order)."""
+    rng = np.random.default_rng(2000 + chr_count)
+    chr_list = gen_rand_chr_list(rng, chr_count)
+    text = gen_rand_text(rng, chr_list, 100, 300)
+    patterns = [gen_rand_pattern(rng, text, 1, 10) for _ in range(100)]
+    symbols = [bytes([c]) for c in chr_list]
+    for (p, n, v) in ALL_TYPES:
+        if (1 << n) < chr_count:
+            continue
+        ora, gpu, table, _ = _pair(oracle, fm, text, symbols, p, n, v, 3, 2)
+        enc_text = table[np.frombuffer(text, dtype=np.uint8)]
+        offs, pos = gpu.locate_batch(patterns, sorted_=True)
+        for i, pat in enumerate(patterns):
+            ans = brute_force_locate(enc_text, table[np.frombuffer(pat, dtype=np.uint8)])
+            assert np.array_equal(pos[int(offs[i]):int(offs[i + 1])].astype(np.uint64), ans), (p, n, v, pat)
+        _check_batch(ora, gpu, patterns[:40])
+        gpu.close()
+
+
+def test_config_invariance(oracle, fm):
+    """config_invariance/mod.rs:51-143: kLTS {None,2,3,4} x SA {Uncompressed,2,3,4} x every type."""
+    rng = np.random.default_rng(43)
+    text = gen_rand_text(rng, b"ACGT", 1000, 1000)
+    patterns = [gen_rand_pattern(rng, text, 10, 10)] + [gen_rand_pattern(rng, text, 1, 6) for _ in range(7)]
+    symbols = [b"A", b"C", b"G", b"T"]
+    base = None
+    for k in (1, 2, 3, 4):
+        for r in (1, 2, 3, 4):
+            for (p, n, v) in ALL_TYPES:
+                ora, gpu, _, _ = _pair(oracle, fm, text, symbols, p, n, v, k, r)
+                offs, pos = gpu.locate_batch(patterns, sorted_=True)
+                ans = [pos[int(offs[i]):int(offs[i + 1])].astype(np.uint64) for i in range(len(patterns))]
+                if base is None:
+                    base = ans
+                    _check_batch(ora, gpu, patterns)
+                for a, b in zip(ans, base):
+                    assert np.array_equal(a, b), (k, r, p, n, v)
+                gpu.close()
+
+
+def test_text_encoders_are_consistent(oracle, fm):
+    """text_encoders_consistency/mod.rs:86-106: slice == rev iter; EncodingTable == PassThrough."""
+    rng = np.random.default_rng(4)
+    for chr_count, types in ((4, [(32, 2, 64), (64, 3, 32)]), (21, [(32, 5, 64), (64, 6, 128)])):
+        chr_list = gen_rand_chr_list(rng, chr_count)
+        text = gen_rand_text(rng, chr_list, 300, 500)
+        symbols = [bytes([c]) for c in chr_list]
+        patterns = [gen_rand_pattern(rng, text, 1, 12) for _ in range(64)]
+        for (p, n, v) in types:
+            ora_t, gpu_t, table, _ = _pair(oracle, fm, text, symbols, p, n, v, 3, 2)
+            ora_p, gpu_p, _, _ = _pair(oracle, fm, text, symbols, p, n, v, 3, 2, passthrough=True)
+            enc = [bytes(table[np.frombuffer(q, dtype=np.uint8)]) for q in patterns]
+            _check_batch(ora_t, gpu_t, patterns)
+            _check_batch(ora_t, gpu_t, [q[::-1] for q in patterns], reversed_=True)
+            _check_batch(ora_p, gpu_p, enc)
+            _check_batch(ora_p, gpu_p, [q[::-1] for q in enc], reversed_=True)
+            ot, pt = gpu_t.locate_batch(patterns)
+            op, pp = gpu_p.locate_batch(enc)
+            assert np.array_equal(ot, op) and np.array_equal(pt, pp)
+            assert np.array_equal(gpu_t.count_batch(patterns), gpu_t.count_batch([q[::-1] for q in patterns], reversed_=True))
+
+
+@pytest.mark.parametrize("vec_bits", [32, 64, 128])
+def test_edge_cases(oracle, fm, vec_bits):
+    """SURVEY.md Appendix B on the GPU."""
+    rng = np.random.default_rng(12 + vec_bits)
+    symbols = [b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"]
+    for n in (vec_bits * 4, vec_bits, vec_bits - 1, vec_bits + 1, 1, 2, 3):
+        text = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)])
+        for k, r in ((1, 1), (3, 2), (4, 5)):
+            ora, gpu, _, _ = _pair(oracle, fm, text, symbols, 32, 3, vec_bits, k, r)
+            pats = {text[i:i + m] for i in range(0, n, max(1, n // 7)) for m in (1, 2, 3, 4, 9) if i + m <= n}
+            pats |= {b"A", b"AC", b"ACG", b"TTTTTTTT", b"N", b"NN", b"xyz", b"GATTACA", b"a", b"acgt"}
+            _check_batch(ora, gpu, sorted(pats))
+            gpu.close()
+    # homopolymer: one pattern with hundreds of rows, LF walks that hit the sentinel row
+    ora, gpu, _, _ = _pair(oracle, fm, b"A" * 777, [b"A", b"C", b"G", b"T"], 64, 2, vec_bits, 2, 3)
+    _check_batch(ora, gpu, [b"AAAA", b"A", b"C", b"AC", b"A" * 777, b"A" * 778])
+    assert gpu.count(b"AAAA") == 774
+    # empty pattern: reference panics (count_array.rs:211) -> error code, nothing computed
+    with pytest.raises(fm.EmptyPattern):
+        gpu.count(b"")
+    with pytest.raises(fm.EmptyPattern):
+        gpu.count_batch([b"A", b"", b"C"])
+    with pytest.raises(fm.EmptyPattern):
+        gpu.locate_batch([b"A", b""])
+    # empty batch
+    assert gpu.count_batch([]).size == 0
+    offs, pos = gpu.locate_batch([])
+    assert list(offs) == [0] and pos.size == 0
+    # PassThrough byte >= symbol_count: caller error in the reference (silent wrong row); an error here
+    ora_p, gpu_p, _, _ = _pair(oracle, fm, b"ACGTACGT", [b"A", b"C", b"G", b"T"], 32, 2, vec_bits, 1, 1, passthrough=True)
+    with pytest.raises(fm.SvfmError) as e:
+        gpu_p.count_batch([bytes([0, 1]), bytes([9, 1])])
+    assert e.value.code == 24
+
+
+def test_load_errors(oracle, fm):
+    po = oracle
+    table, sc = po.encoding_table([b"A", b"C", b"G", b"T"])
+    t = po.IndexType(32, 2, 64, True)
+    ft = fm.IndexType(32, 2, 64, True)
+    blob = po.build_blob(t, b"ACGTACGTTTGACCA", sc, table, 2, 2)
+    bad = blob.copy()
+    bad[1] = ord("x")
+    with pytest.raises(fm.InvalidFormat):
+        fm.FmIndex.load(bad, ft)
+    longer = np.concatenate([blob, np.zeros(8, dtype=np.uint8)])
+    with pytest.raises(fm.MismatchedBlobSize) as e:
+        fm.FmIndex.load(longer, ft)
+    assert (e.value.expected, e.value.actual) == (blob.size, blob.size + 8)
+    with pytest.raises(fm.MismatchedBlobSize):
+        fm.FmIndex.load(blob, fm.IndexType(64, 2, 64, True))
+    with pytest.raises(fm.InvalidFormat):
+        fm.FmIndex.load(blob[:64], ft)
+    ix = fm.FmIndex.load(blob, ft)
+    assert ix.count(b"ACG") == 2
+
+
+def test_medium_random_batch(oracle, fm):
+    """cfg1-shaped index at 2 Mbp: u32, Block3<u64>, S=5, r=2, k=3, 20 bp patterns cut from the text plus
+    absent / short / long / wildcard patterns, compared with the oracle's pattern-parallel driver."""
+    po = oracle
+    rng = np.random.default_rng(42)
+    n = 2_000_000
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)]
+    text = text.copy()
+    text[rng.integers(0, n, size=2000)] = ord("N")
+    table, sc = po.encoding_table([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
+    t = po.IndexType(32, 3, 64, True)
+    blob = po.build_blob(t, text, sc, table, 3, 2)
+    ora = po.OracleFmIndex.load(blob, t)
+    gpu = fm.FmIndex.load(blob, fm.IndexType(32, 3, 64, True))
+    for ln, m in ((20, 200_000), (6, 50_000), (1, 256), (2, 256), (150, 20_000)):
+        starts = rng.integers(0, n - ln, size=m)
+        pats = text[starts[:, None] + np.arange(ln)[None, :]]
+        if ln == 20:
+            pats[::7, 3] = ord("A")  # mutate some patterns so that many are absent (early exit path)
+        ocounts, ooffs, opos, ock = ora.locate_batch(pats, threads=os.cpu_count() or 1)
+        counts = gpu.count_batch(pats)
+        offs, pos = gpu.locate_batch(pats)
+        assert np.array_equal(counts.astype(np.uint64), ocounts)
+        assert np.array_equal(offs, ooffs)
+        assert np.array_equal(pos, opos)
+        offs_s, pos_s = gpu.locate_batch(pats, sorted_=True)
+        assert np.array_equal(offs_s, ooffs)
+        idx = np.repeat(np.arange(m, dtype=np.uint64), np.diff(ooffs).astype(np.int64))
+        exp_sorted = opos[np.lexsort((opos, idx))]
+        assert np.array_equal(pos_s, exp_sorted)
+        ck = int((((pos.astype(np.uint64) + np.uint64(1)) * (np.uint64(2) * idx + np.uint64(1)))).sum(dtype=np.uint64))
+        assert ck == ock
+    # u64 positions + Block2<u128> + sampling ratio 16 + non-power-of-two ratio
+    for (p, nn, v, k, r) in ((64, 2, 128, 2, 16), (64, 3, 64, 3, 5), (32, 6, 32, 1, 7)):
+        sub = text[:300_000]
+        sub = np.where(sub == ord("N"), ord("A"), sub).astype(np.uint8)
+        tb, s2 = po.encoding_table([b"A", b"C", b"G", b"T"])
+        tt = po.IndexType(p, nn, v, True)
+        b2 = po.build_blob(tt, sub, s2, tb, k, r)
+        o2 = po.OracleFmIndex.load(b2, tt)
+        g2 = fm.FmIndex.load(b2, fm.IndexType(p, nn, v, True))
+        starts = rng.integers(0, len(sub) - 9, size=30_000)
+        pats = sub[starts[:, None] + np.arange(9)[None, :]]
+        oc, oo, op_, _ = o2.locate_batch(pats, threads=os.cpu_count() or 1)
+        offs, pos = g2.locate_batch(pats)
+        assert np.array_equal(offs, oo) and np.array_equal(pos, op_)
+        assert np.array_equal(g2.count_batch(pats).astype(np.uint64), oc)

@@ -1,0 +1,112 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/svfm.h declares,
+the host-only parts (blob validation, blob_size, error mapping) behave like the reference, and the
+product fails loudly without a CUDA device.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fm():
+    import __graft_entry__ as ge
+    import sview_fmindex_b200 as fm
+    from sview_fmindex_b200 import _ffi
+    if not os.path.exists(_ffi.LIB_PATH):
+        ge.build()
+    return fm
+
+
+def test_library_exports_every_declared_symbol(fm):
+    from sview_fmindex_b200 import _ffi
+    hdr = open(os.path.join(ROOT, "include", "svfm.h")).read()
+    declared = set(re.findall(r"\b(svfm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"svfm_host_alloc"} - declared
+    lib = C.CDLL(_ffi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libsvfm.so does not export {name}"
+    bound = {e[0] for e in _ffi.EXPORTS}
+    assert declared == bound, (declared - bound, bound - declared)
+    assert b"sm_100a" in _ffi.lib().svfm_version()
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or load it."""
+    pkg = os.path.join(ROOT, "sview_fmindex_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                for needle in ("pyoracle", "fm_oracle", "libfm_oracle", "from oracle", "import oracle"):
+                    assert needle not in src.replace("never imported", ""), (f, needle)
+
+
+def test_blob_size_matches_reference_layout(fm, oracle):
+    po = oracle
+    enc = fm.EncodingTable.from_symbols([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
+    assert enc.symbol_count() == 5
+    b = fm.FmIndexBuilder.new(10**9, 5, enc, fm.IndexType(32, 3, 64, True)) \
+        .set_lookup_table_config(fm.LookupTableConfig.KmerSize(3)) \
+        .set_suffix_array_config(fm.SuffixArrayConfig.Compressed(2))
+    assert b.blob_size() == 2_687_501_296
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        p = int(rng.choice([32, 64])); n = int(rng.integers(2, 7)); v = int(rng.choice([32, 64, 128]))
+        e = bool(rng.integers(0, 2)); S = int(rng.integers(1, (1 << n) + 1)); k = int(rng.integers(1, 4))
+        r = int(rng.integers(1, 9)); tl = int(rng.integers(1, 10**7))
+        ft = fm.IndexType(p, n, v, e)
+        bb = fm.FmIndexBuilder(tl, S, fm.EncodingTable(np.zeros(256, dtype=np.uint8)) if e else None, ft)
+        bb.kmer_size, bb.sampling_ratio = k, r
+        assert bb.blob_size() == po.blob_layout(po.IndexType(p, n, v, e), tl, S, k, r).total_size
+    with pytest.raises(fm.BuildError) as ei:
+        fm.FmIndexBuilder.new(100, 5, fm.EncodingTable.from_symbols([b"A"] * 5), fm.IndexType(32, 2, 64, True))
+    assert ei.value.code == 10 and ei.value.detail == (4, 5)  # SymbolCountOver(max, got), builder/mod.rs:71-73
+    with pytest.raises(fm.BuildError):
+        fm.FmIndexBuilder.new(100, 4, enc, fm.IndexType(32, 3, 64, True)).set_lookup_table_config(fm.LookupTableConfig.KmerSize(1))
+    with pytest.raises(fm.BuildError):
+        fm.FmIndexBuilder.new(100, 4, enc, fm.IndexType(32, 3, 64, True)).set_suffix_array_config(fm.SuffixArrayConfig.Compressed(1))
+    mm = fm.FmIndexBuilder.new(100, 4, enc, fm.IndexType(32, 3, 64, True)).set_lookup_table_config(fm.LookupTableConfig.MaxMemory(4 * 5**6))
+    assert mm.kmer_size == 6
+
+
+def test_encoding_table_mirror(fm, oracle):
+    for syms in ([b"Aa", b"Cc", b"Gg", b"Tt"], [b"ACD", b"x"], [bytes([i]) for i in range(40, 61)]):
+        for wc in (False, True):
+            mine = fm.EncodingTable.from_symbols_with_wildcard(syms) if wc else fm.EncodingTable.from_symbols(syms)
+            tbl, sc = oracle.encoding_table(syms, wc)
+            assert np.array_equal(mine.table, tbl) and mine.symbol_count() == sc
+
+
+def test_check_blob_is_the_load_error_path(fm, oracle):
+    po = oracle
+    table, sc = po.encoding_table([b"A", b"C", b"G", b"T"])
+    for (p, n, v) in ((32, 2, 64), (64, 3, 128), (32, 6, 32)):
+        blob = po.build_blob(po.IndexType(p, n, v, True), b"ACGTACGTTTGACCAGGATTACA", sc, table, 2, 3)
+        ft = fm.IndexType(p, n, v, True)
+        info = fm.FmIndex.check_blob(blob, ft)
+        assert (info.text_len, info.symbol_count, info.kmer_size, info.sampling_ratio) == (23, 4, 2, 3)
+        bad = blob.copy(); bad[3] = ord("9")
+        with pytest.raises(fm.InvalidFormat):
+            fm.FmIndex.check_blob(bad, ft)
+        with pytest.raises(fm.MismatchedBlobSize) as e:
+            fm.FmIndex.check_blob(blob[:-8 if v != 128 else -16], ft)
+        assert e.value.expected == blob.size
+        with pytest.raises(fm.InvalidFormat):
+            fm.FmIndex.check_blob(blob[:40], ft)
+
+
+def test_no_cpu_fallback(fm, oracle):
+    """Without a CUDA device every compute entry point must fail loudly (SVFM_ERR_CUDA), never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    po = oracle
+    table, sc = po.encoding_table([b"A", b"C", b"G", b"T"])
+    blob = po.build_blob(po.IndexType(32, 2, 64, True), b"ACGTACGT", sc, table)
+    with pytest.raises(fm.SvfmError) as e:
+        fm.FmIndex.load(blob, fm.IndexType(32, 2, 64, True))
+    assert e.value.code == 30
