@@ -77,6 +77,18 @@ EXPORTS = [
     ("svfm_build_device", C.c_int, [SvfmType, _vp, C.c_uint64, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.c_int, _vp, C.c_uint64, _u64p]),
 ]
 
+# include/svfm_bench.h (measurement / self-check helpers)
+_dp = C.POINTER(C.c_double)
+BENCH_EXPORTS = [
+    ("svfm_bench_synth_text", C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, C.c_uint32, C.c_uint8, _vp]),
+    ("svfm_bench_synth_patterns", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint64, _vp]),
+    ("svfm_bench_gather32", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _dp, _vp]),
+    ("svfm_bench_verify_locate", C.c_int, [_vp, C.c_uint64, _vp, C.c_uint32, C.c_uint64, _vp, _vp, _vp, C.c_uint32,
+                                           _vp, _u64p, _u64p, _vp]),
+    ("svfm_bench_count_digest", C.c_int, [_vp, C.c_uint32, C.c_uint64, _u64p, _u64p, _vp]),
+    ("svfm_bench_flush_l2", C.c_int, [_vp, C.c_uint64, _vp]),
+]
+
 _lib = None
 
 
@@ -88,7 +100,7 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C sview_fmindex_b200/csrc` (there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
-        for name, restype, argtypes in EXPORTS:
+        for name, restype, argtypes in EXPORTS + BENCH_EXPORTS:
             fn = getattr(L, name)
             fn.restype = restype
             fn.argtypes = argtypes

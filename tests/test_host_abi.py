@@ -23,14 +23,15 @@ def fm():
 
 def test_library_exports_every_declared_symbol(fm):
     from sview_fmindex_b200 import _ffi
-    hdr = open(os.path.join(ROOT, "include", "svfm.h")).read()
-    declared = set(re.findall(r"\b(svfm_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"svfm_host_alloc"} - declared
     lib = C.CDLL(_ffi.LIB_PATH)
-    for name in sorted(declared):
-        assert hasattr(lib, name), f"libsvfm.so does not export {name}"
-    bound = {e[0] for e in _ffi.EXPORTS}
-    assert declared == bound, (declared - bound, bound - declared)
+    for header, table in (("svfm.h", _ffi.EXPORTS), ("svfm_bench.h", _ffi.BENCH_EXPORTS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        declared = set(re.findall(r"\b(svfm_[a-z0-9_]+)\s*\(", hdr))
+        assert declared
+        for name in sorted(declared):
+            assert hasattr(lib, name), f"libsvfm.so does not export {name}"
+        bound = {e[0] for e in table}
+        assert declared == bound, (header, declared - bound, bound - declared)
     assert b"sm_100a" in _ffi.lib().svfm_version()
 
 
