@@ -144,9 +144,29 @@ int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint6
                              uint32_t fixed_len, uint32_t flags, uint64_t* d_out_offs,
                              void** d_positions, uint64_t* total);
 
+/* ---- per-phase device timing of a session (CUDA events on the session's stream) --------------------
+ * Phases of the batch pipelines; ms[] = summed device time of the phase's kernels since the last reset,
+ * launches[] = kernels launched in the phase.  Reading synchronises the session's stream. */
+enum {
+    SVFM_PHASE_PRESORT = 0, /* pattern encoding/packing + locality sort of the batch */
+    SVFM_PHASE_SEARCH = 1,  /* backward-search kernel (count) */
+    SVFM_PHASE_SCAN = 2,    /* exclusive prefix sum of the counts -> CSR offsets */
+    SVFM_PHASE_LOCATE = 3,  /* LF-walk + sampled-SA lookup kernel */
+    SVFM_PHASE_SEGSORT = 4, /* optional per-pattern sort of the positions (SVFM_SORTED) */
+    SVFM_PHASE_OTHER = 5,   /* permutation / scatter helpers */
+    SVFM_PHASE_MAX = 8
+};
+int svfm_session_set_timing(svfm_session* s, int enabled);
+int svfm_session_get_timing(svfm_session* s, double ms[SVFM_PHASE_MAX], uint64_t launches[SVFM_PHASE_MAX], int reset);
+
 /* ---- misc -------------------------------------------------------------------------------------- */
 void* svfm_host_alloc(size_t bytes);  /* pinned host memory (cudaHostAlloc) or NULL */
 void svfm_host_free(void* p);
+/* Process-wide tuning knobs.  SVFM_TUNE_SORT_MIN: batches with at least this many patterns are
+ * locality-sorted by their trailing symbols before the search (0 = always, UINT64_MAX = never; default
+ * 131072, or the SVFM_SORT_MIN environment variable).  Results never depend on it. */
+enum { SVFM_TUNE_SORT_MIN = 0 };
+int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */
 uint64_t svfm_launch_count(void);     /* kernels launched by this library since process start */
 const char* svfm_version(void);

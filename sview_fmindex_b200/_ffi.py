@@ -28,6 +28,7 @@ SVFM_ERR_CAPACITY = 25
 SVFM_ERR_BAD_ARG = 26
 SVFM_ERR_CUDA = 30
 
+SVFM_TUNE_SORT_MIN = 0
 SVFM_REVERSED = 1
 SVFM_SORTED = 2
 
@@ -67,8 +68,11 @@ EXPORTS = [
     ("svfm_session_stream", _vp, [_vp]),
     ("svfm_count_batch_device", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     ("svfm_locate_batch_device", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, C.POINTER(_vp), _u64p]),
+    ("svfm_session_set_timing", C.c_int, [_vp, C.c_int]),
+    ("svfm_session_get_timing", C.c_int, [_vp, C.POINTER(C.c_double), _u64p, C.c_int]),
     ("svfm_host_alloc", _vp, [C.c_size_t]),
     ("svfm_host_free", None, [_vp]),
+    ("svfm_set_tuning", C.c_int, [C.c_int, C.c_uint64]),
     ("svfm_last_error", C.c_char_p, []),
     ("svfm_launch_count", C.c_uint64, []),
     ("svfm_version", C.c_char_p, []),

@@ -52,7 +52,8 @@ __global__ void gather32_kernel(const uint4* __restrict__ buf, uint64_t sectors,
         uint4 a[GATHER_ILP], b[GATHER_ILP];
 #pragma unroll
         for (int u = 0; u < GATHER_ILP; u++) {
-            const uint64_t s = hash_at(seed, base + u) % sectors;
+            // multiply-shift range reduction (a 64-bit modulo would make the kernel ALU-bound)
+            const uint64_t s = __umul64hi(hash_at(seed, base + u), sectors);
             const uint4* p = buf + s * 2;
             asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(p));

@@ -17,6 +17,7 @@ struct PatternBatch {
 };
 
 constexpr int SEARCH_THREADS = 256;
+constexpr uint32_t HEAVY_ROWS = 1024;  // patterns with more SA rows than this are located row-parallel
 
 // One backward-search step for both range ends: FmIndex::next_pos_range (locate/mod.rs:39-45) =
 // count_array[s] + get_next_rank(pos, s) (bwm/mod.rs:197-215) for pos in {sp, ep}.
@@ -52,12 +53,48 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, const P* __
     }
 }
 
+// Locality key of a pattern = its trailing symbols packed `bits` per symbol from the top of a u64, the
+// LAST symbol most significant (backward search consumes the pattern from its end, so patterns that share
+// a suffix walk the same checkpoint rows and blocks for as many steps as the shared suffix is long).
+// The key doubles as the encoded pattern: the search kernel takes the last min(len, 64/bits) symbols from
+// it and never touches the pattern bytes again unless the pattern is longer.  Also validates the batch.
+__global__ void __launch_bounds__(SEARCH_THREADS)
+pack_keys_kernel(const uint8_t* __restrict__ table, uint32_t S, const PatternBatch pb, uint32_t bits,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ err) {
+    __shared__ uint8_t s_table[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = table ? table[i] : (uint8_t)i;
+    __syncthreads();
+    const uint32_t m = 64u / bits;
+    int errbits = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pb.n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t base, len;
+        if (pb.offs) { base = pb.offs[i]; len = pb.offs[i + 1] - base; }
+        else { base = i * (uint64_t)pb.fixed_len; len = pb.fixed_len; }
+        const uint8_t* p = pb.pats + base;
+        if (len == 0) errbits |= ERRBIT_EMPTY_PATTERN;
+        const uint32_t take = len < m ? (uint32_t)len : m;
+        uint64_t key = 0;
+        for (uint32_t j = 0; j < take; j++) {
+            const uint64_t fwd = len - 1 - j;  // j-th symbol from the end
+            uint32_t s = s_table[__ldg(p + (pb.reversed ? (len - 1 - fwd) : fwd))];
+            if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
+            key |= (uint64_t)s << (64u - bits * (j + 1));
+        }
+        keys[i] = key;
+        vals[i] = (uint32_t)i;
+    }
+    if (errbits) atomicOr(err, errbits);
+}
+
 // FmIndex::get_pos_range (locate/with_slice.rs:21-33) for one pattern per thread, grid-stride.
-// Writes sp_out[i] (may be NULL) and cnt_out[i] = ep - sp.
+// Work item w handles pattern idx[w] (idx == NULL: identity).  With keys != NULL the last 64/bits symbols of
+// the pattern come out of keys[w] (see pack_keys_kernel).  Outputs in WORK order, coalesced:
+// sp_work[w] (nullable) and cnt_work[w] = ep - sp.
 template <class P, int NPL, int VBITS>
 __global__ void __launch_bounds__(SEARCH_THREADS)
-search_kernel(const DevIndex<P> ix, const PatternBatch pb, P* __restrict__ sp_out, P* __restrict__ cnt_out,
-              int* __restrict__ err) {
+search_kernel(const DevIndex<P> ix, const PatternBatch pb, const uint64_t* __restrict__ keys,
+              const uint32_t* __restrict__ idx, uint32_t bits, P* __restrict__ sp_work, P* __restrict__ cnt_work,
+              unsigned long long* __restrict__ heavy_seen, int* __restrict__ err) {
     __shared__ uint8_t s_table[256];
     __shared__ P s_count[65];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = ix.table ? ix.table[i] : (uint8_t)i;
@@ -66,8 +103,12 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, P* __restrict__ sp_ou
 
     const uint32_t S = ix.symbol_count;
     const uint32_t k = ix.kmer_size;
+    const uint32_t in_key = keys ? 64u / bits : 0u;  // symbols (from the end) available in the key
+    const uint64_t sym_mask = (1ull << bits) - 1;
     int errbits = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pb.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < pb.n; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = idx ? (uint64_t)idx[w] : w;
+        const uint64_t key = keys ? keys[w] : 0ull;
         uint64_t base, len;
         if (pb.offs) { base = pb.offs[i]; len = pb.offs[i + 1] - base; }
         else { base = i * (uint64_t)pb.fixed_len; len = pb.fixed_len; }
@@ -78,34 +119,37 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, P* __restrict__ sp_ou
         } else {
             // logical (forward) symbol j of the pattern
             auto sym_at = [&](uint64_t j) -> uint32_t {
-                uint32_t s = s_table[__ldg(p + (pb.reversed ? (len - 1 - j) : j))];
+                const uint64_t from_end = len - 1 - j;
+                if (from_end < in_key) return (uint32_t)((key >> (64u - bits * ((uint32_t)from_end + 1))) & sym_mask);
+                uint32_t s = s_table[__ldg(p + (pb.reversed ? from_end : j))];
                 if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
                 return s;
             };
             // CountArrayView::get_initial_pos_range_and_idx_of_pattern (count_array.rs:203-233)
-            uint64_t idx;
+            uint64_t pi;
             if (len < k) {
                 uint64_t start = 0;
                 for (uint64_t j = 0; j < len; j++) start += (uint64_t)(sym_at(j) + 1) * __ldg(ix.kmer_multiplier + j);
                 const uint64_t end = start + __ldg(ix.kmer_multiplier + (len - 1)) - 1;
                 sp = __ldg(ix.kmer_count_table + (start - 1));
                 ep = __ldg(ix.kmer_count_table + end);
-                idx = 0;
+                pi = 0;
             } else {
                 uint64_t start = 0;
                 for (uint32_t j = 0; j < k; j++) start += (uint64_t)(sym_at(len - k + j) + 1) * __ldg(ix.kmer_multiplier + j);
                 sp = __ldg(ix.kmer_count_table + (start - 1));
                 ep = __ldg(ix.kmer_count_table + start);
-                idx = len - k;
+                pi = len - k;
             }
             // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
-            while (sp < ep && idx > 0) {
-                idx -= 1;
-                backward_step<P, NPL, VBITS>(ix, s_count, sym_at(idx), sp, ep);
+            while (sp < ep && pi > 0) {
+                pi -= 1;
+                backward_step<P, NPL, VBITS>(ix, s_count, sym_at(pi), sp, ep);
             }
         }
-        if (sp_out) sp_out[i] = sp;
-        cnt_out[i] = (P)(ep - sp);
+        if (sp_work) sp_work[w] = sp;
+        cnt_work[w] = (P)(ep - sp);
+        if ((uint64_t)(ep - sp) > HEAVY_ROWS) atomicAdd(heavy_seen, 1ull);  // rare: sizes the heavy list
     }
     if (errbits) atomicOr(err, errbits);
 }
@@ -143,25 +187,115 @@ __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restri
 
 constexpr int LOCATE_THREADS = 256;
 
-// One thread per output slot t in [0, total): slot t belongs to the pattern i with
-// out_offs[i] <= t < out_offs[i+1] and is SA row sp[i] + (t - out_offs[i]), which reproduces the
-// reference's output order (for pos in sp..ep, locate/mod.rs:19).  The per-block window of candidate
-// patterns is found once with two binary searches; each thread then searches only that window.
+template <class P>
+struct HeavyList {
+    P* sp;                    // first SA row of the pattern
+    P* cnt;                   // number of rows
+    uint64_t* obase;          // where its positions start in the output
+    uint32_t* pat;            // its pattern index (record mode)
+    unsigned long long* n;    // entries appended so far
+    uint64_t capacity;
+};
+
+// Locate for patterns in work order: work item w has SA rows sp_work[w] .. +cnt_work[w] and writes the
+// position of row sp+j at positions[offs[w] + j] (offs = exclusive prefix sums of cnt_work), i.e. in SA-row
+// order inside a pattern (the reference's order, locate/mod.rs:19).  In record mode (rec_key != NULL) it also
+// writes rec_key[offs[w] + j] = idx[w], the caller's pattern index, so that a stable sort by rec_key brings
+// the positions into the caller's CSR order without any random scatter.
+// One warp owns 32 consecutive work items and spreads ALL their rows over its lanes (warp prefix sum of the
+// counts, then each lane finds the owner of its row with a shuffle binary search), so a pattern with many
+// rows does not serialise one lane.  Patterns with more than HEAVY_ROWS rows are deferred to
+// locate_rows_kernel through the heavy list.
 template <class P, int NPL, int VBITS>
 __global__ void __launch_bounds__(LOCATE_THREADS)
-locate_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_t* __restrict__ out_offs, uint64_t n,
-              uint64_t total, P* __restrict__ positions) {
+locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
+                   const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
+                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy) {
+    __shared__ P s_count[65];
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w0 = warp_id * 32; w0 < n; w0 += n_warps * 32) {
+        const uint64_t w = w0 + lane;
+        uint32_t c = 0;
+        P sp = 0;
+        uint64_t obase = 0;
+        uint32_t pat = 0;
+        if (w < n) {
+            const P cw = cnt_work[w];
+            if (cw != 0) {
+                sp = sp_work[w];
+                obase = offs[w];
+                pat = idx ? idx[w] : (uint32_t)w;
+                if ((uint64_t)cw > HEAVY_ROWS) {
+                    const unsigned long long h = atomicAdd(heavy.n, 1ull);
+                    if (h < heavy.capacity) { heavy.sp[h] = sp; heavy.cnt[h] = cw; heavy.obase[h] = obase; heavy.pat[h] = pat; }
+                } else {
+                    c = (uint32_t)cw;
+                }
+            }
+        }
+        if (__all_sync(full, c <= 1u)) {
+            // common case: at most one row per pattern, no redistribution needed
+            if (c) {
+                positions[obase] = locate_row<P, NPL, VBITS>(ix, s_count, sp);
+                if (rec_key) rec_key[obase] = pat;
+            }
+            continue;
+        }
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(full, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const uint32_t excl = incl - c;
+        const uint32_t total = __shfl_sync(full, incl, 31);
+        for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            // owner = first lane whose inclusive sum exceeds r
+            int o = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(full, incl, o + step - 1);
+                if (v <= r) o += step;
+            }
+            o &= 31;
+            const uint32_t e = __shfl_sync(full, excl, o);
+            const P osp = __shfl_sync(full, sp, o);
+            const uint64_t oo = __shfl_sync(full, obase, o);
+            const uint32_t opat = __shfl_sync(full, pat, o);
+            if (r < total) {
+                const uint32_t j = r - e;
+                positions[oo + j] = locate_row<P, NPL, VBITS>(ix, s_count, (P)(osp + (P)j));
+                if (rec_key) rec_key[oo + j] = opat;
+            }
+        }
+    }
+}
+
+// Row-parallel locate for the heavy list: one thread per SA row; row t belongs to the entry h with
+// offs[h] <= t < offs[h+1].  The per-block window of candidate entries is found once with two binary
+// searches; each thread then searches only that window.
+template <class P, int NPL, int VBITS>
+__global__ void __launch_bounds__(LOCATE_THREADS)
+locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_t* __restrict__ offs,
+                   const uint64_t* __restrict__ obase, const uint32_t* __restrict__ pat, uint64_t n, uint64_t total,
+                   P* __restrict__ positions, uint32_t* __restrict__ rec_key) {
     __shared__ P s_count[65];
     __shared__ uint64_t s_win[2];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     const uint64_t t0 = (uint64_t)blockIdx.x * LOCATE_THREADS;
     if (threadIdx.x < 2) {
-        // largest i in [0, n) with out_offs[i] <= target
+        // largest i in [0, n) with offs[i] <= target
         uint64_t target = threadIdx.x == 0 ? t0 : (t0 + LOCATE_THREADS - 1 < total ? t0 + LOCATE_THREADS - 1 : total - 1);
-        uint64_t lo = 0, hi = n;  // invariant: out_offs[lo] <= target < out_offs[hi]
+        uint64_t lo = 0, hi = n;  // invariant: offs[lo] <= target < offs[hi]
         while (hi - lo > 1) {
             uint64_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(out_offs + mid) <= target) lo = mid; else hi = mid;
+            if (__ldg(offs + mid) <= target) lo = mid; else hi = mid;
         }
         s_win[threadIdx.x] = lo;
     }
@@ -171,10 +305,23 @@ locate_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_t* __
     uint64_t lo = s_win[0], hi = s_win[1] + 1;
     while (hi - lo > 1) {
         uint64_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(out_offs + mid) <= t) lo = mid; else hi = mid;
+        if (__ldg(offs + mid) <= t) lo = mid; else hi = mid;
     }
-    const P row = (P)(__ldg(sp + lo) + (P)(t - __ldg(out_offs + lo)));
-    positions[t] = locate_row<P, NPL, VBITS>(ix, s_count, row);
+    const uint64_t j = t - __ldg(offs + lo);
+    const P row = (P)(__ldg(sp + lo) + (P)j);
+    const uint64_t dst = __ldg(obase + lo) + j;
+    positions[dst] = locate_row<P, NPL, VBITS>(ix, s_count, row);
+    if (rec_key) rec_key[dst] = __ldg(pat + lo);
+}
+
+// CSR offsets from the pattern indices of the records once they are sorted by pattern: first[k] = index of
+// the first record of pattern k (patterns without records keep the 0xff.. fill); out_offs is then the
+// reverse running minimum of `first` with out_offs[n] = total (done with a device scan by the caller).
+__global__ void run_starts_kernel(const uint32_t* __restrict__ sorted_key, uint64_t total, uint64_t* __restrict__ first) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = sorted_key[t];
+        if (t == 0 || sorted_key[t - 1] != k) first[k] = t;
+    }
 }
 
 }  // namespace svfm

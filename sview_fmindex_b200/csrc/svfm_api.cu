@@ -9,9 +9,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_segmented_sort.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/reverse_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include "blob_layout.h"
@@ -37,6 +38,7 @@ struct svfm_index {
     uint64_t blob_len = 0;
     uint64_t text_len = 0;
     uint64_t sentinel_index = 0;
+    uint32_t symbols_present = 0;  // symbols with at least one occurrence in the text (from count_array)
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
 };
@@ -44,9 +46,20 @@ struct svfm_index {
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer pats, offs, sp, cnt, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
+    svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
+    svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
+    unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
     int* d_err = nullptr;
     uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
+    // per-phase timing (svfm_session_set_timing)
+    bool timing = false;
+    struct Span { int phase; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double phase_ms[SVFM_PHASE_MAX] = {0};
+    uint64_t phase_launches[SVFM_PHASE_MAX] = {0};
 };
 
 namespace svfm {
@@ -86,6 +99,18 @@ static int finish_load(svfm_index* ix) {
     const uint64_t P = ix->type.pos_bits / 8;
     SVFM_CUDA(cudaMemcpy(&v, ix->d_blob + L.off_count_array + (uint64_t)(L.count_array_len - 1) * P, P, cudaMemcpyDeviceToHost));
     ix->text_len = v;
+    {
+        uint8_t ca[65 * 8] = {0};
+        SVFM_CUDA(cudaMemcpy(ca, ix->d_blob + L.off_count_array, (uint64_t)L.count_array_len * P, cudaMemcpyDeviceToHost));
+        uint64_t prev = 0;
+        ix->symbols_present = 0;
+        for (uint32_t i = 1; i < L.count_array_len; i++) {
+            uint64_t c = 0;
+            std::memcpy(&c, ca + i * P, P);
+            if (c > prev) ix->symbols_present++;
+            prev = c;
+        }
+    }
     v = 0;
     SVFM_CUDA(cudaMemcpy(&v, ix->d_blob + L.off_sentinel_index, P, cudaMemcpyDeviceToHost));
     ix->sentinel_index = v;
@@ -156,7 +181,8 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     s->ix = ix;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_err, sizeof(int));
-    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 4 * sizeof(uint64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(uint64_t), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         g_last_error = std::string("session_new: ") + cudaGetErrorString(e);
         delete s;
@@ -166,13 +192,54 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     return SVFM_OK;
 }
 
+static void collect_spans(svfm_session* s);
+
 static void session_delete(svfm_session* s) {
     if (!s) return;
     cudaSetDevice(s->ix->device);
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
     if (s->d_err) cudaFree(s->d_err);
+    if (s->d_counters) cudaFree(s->d_counters);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    collect_spans(s);
+    for (cudaEvent_t e : s->free_events) cudaEventDestroy(e);
     delete s;
+}
+
+// RAII span: records CUDA events around the kernels of one phase when timing is on.
+struct PhaseTimer {
+    svfm_session* s;
+    int phase;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseTimer(svfm_session* s_, int phase_, uint64_t launches) : s(s_), phase(phase_) {
+        s->phase_launches[phase] += launches;
+        g_launches += launches;
+        if (!s->timing) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!s->free_events.empty()) { e = s->free_events.back(); s->free_events.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, s->stream);
+    }
+    ~PhaseTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, s->stream);
+        s->spans.push_back({phase, e0, e1});
+    }
+};
+
+static void collect_spans(svfm_session* s) {
+    for (auto& sp : s->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) s->phase_ms[sp.phase] += ms;
+        s->free_events.push_back(sp.e0);
+        s->free_events.push_back(sp.e1);
+    }
+    s->spans.clear();
 }
 
 struct SessionLease {
@@ -195,6 +262,20 @@ struct SessionLease {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch over the 30 (P, BlockN, Vector) instantiations
 // ---------------------------------------------------------------------------------------------
+// Grid for a grid-stride kernel: exactly the CTAs that can be resident at once (SMs x occupancy), so that
+// there is no partial second wave; fewer when the work does not fill the machine.
+template <class K>
+static int resident_grid(K kernel, uint64_t work_items, int threads, int device) {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
 static int grid_for(uint64_t work_items, int threads, int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -205,12 +286,79 @@ static int grid_for(uint64_t work_items, int threads, int device) {
     return (int)blocks;
 }
 
+// Locality sort of the batch (SVFM_PHASE_PRESORT): patterns ordered by their trailing symbols so that
+// neighbouring threads of the search kernel walk neighbouring checkpoint rows / blocks.  Everything that has
+// to change order afterwards moves through radix sorts (streaming passes), never through random scatters:
+// on B200 one random 32 B sector access costs as much HBM time as streaming ~500 bytes.
+struct SortPlan {
+    bool sorted = false;
+    uint32_t bits = 0;     // bits per symbol in the packed key
+    int begin_bit = 0, end_bit = 64;
+};
+
+static std::atomic<uint64_t> g_sort_min{[] {
+    const char* e = std::getenv("SVFM_SORT_MIN");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 17);
+}()};
+static uint64_t sort_min_patterns() { return g_sort_min.load(); }
+
+static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
+    int b = 0;
+    while (b < 63 && (1ull << b) < n) b++;
+    return b;
+}
+
+static SortPlan plan_sort(const svfm_index* ix, uint64_t n) {
+    SortPlan p;
+    if (n < sort_min_patterns() || n > 0xffffffffull) return p;
+    const uint32_t S = ix->L.symbol_count;
+    p.bits = (uint32_t)bits_for(S);
+    if (p.bits == 0) p.bits = 1;
+    // Sort on as many trailing symbols as it takes to tell the occ blocks apart: log_{S_eff}(blocks) + 1
+    // symbols, S_eff = symbols that actually occur in the text (count_array).
+    const double s_eff = ix->symbols_present > 1 ? (double)ix->symbols_present : 2.0;
+    uint32_t m = 1;
+    double reach = s_eff;
+    while (reach < (double)ix->L.blocks_len && m < 64u / p.bits) { reach *= s_eff; m++; }
+    m = m + 1 < 64u / p.bits ? m + 1 : 64u / p.bits;
+    p.begin_bit = 64 - (int)(m * p.bits);
+    p.end_bit = 64;
+    p.sorted = true;
+    return p;
+}
+
+static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, const uint64_t** keys_out,
+                       const uint32_t** idx_out) {
+    int rc;
+    if ((rc = s->keys0.reserve(pb.n * 8)) || (rc = s->keys1.reserve(pb.n * 8)) || (rc = s->vals0.reserve(pb.n * 4)) ||
+        (rc = s->vals1.reserve(pb.n * 4)))
+        return rc;
+    cub::DoubleBuffer<uint64_t> keys((uint64_t*)s->keys0.ptr, (uint64_t*)s->keys1.ptr);
+    cub::DoubleBuffer<uint32_t> vals((uint32_t*)s->vals0.ptr, (uint32_t*)s->vals1.ptr);
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp, keys, vals, (int64_t)pb.n, plan.begin_bit, plan.end_bit, s->stream));
+    if ((rc = s->cub_temp.reserve(temp))) return rc;
+    const int passes = (plan.end_bit - plan.begin_bit + 7) / 8;
+    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + passes);
+    const svfm_index* ix = s->ix;
+    const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
+    pack_keys_kernel<<<resident_grid(pack_keys_kernel, pb.n, SEARCH_THREADS, ix->device), SEARCH_THREADS, 0, s->stream>>>(
+        table, ix->L.symbol_count, pb, plan.bits, keys.Current(), vals.Current(), s->d_err);
+    SVFM_CUDA(cudaGetLastError());
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, keys, vals, (int64_t)pb.n, plan.begin_bit, plan.end_bit, s->stream));
+    *keys_out = keys.Current();
+    *idx_out = vals.Current();
+    return SVFM_OK;
+}
+
 template <class P, int NPL, int VBITS>
-static int run_search(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) {
+static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
+                      void* d_sp_work, void* d_cnt_work) {
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const int grid = grid_for(pb.n, SEARCH_THREADS, s->ix->device);
-    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, (P*)d_sp, (P*)d_cnt, s->d_err);
-    g_launches++;
+    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, keys, idx, bits, (P*)d_sp_work,
+                                                                        (P*)d_cnt_work, s->d_counters, s->d_err);
     SVFM_CUDA(cudaGetLastError());
     return SVFM_OK;
 }
@@ -231,45 +379,124 @@ static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_
     SVFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_out_offs, n + 1, s->stream));
     int rc = s->cub_temp.reserve(temp);
     if (rc) return rc;
+    PhaseTimer pt(s, SVFM_PHASE_SCAN, 2);
     SVFM_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_temp.ptr, temp, in, d_out_offs, n + 1, s->stream));
-    g_launches += 2;
     return SVFM_OK;
 }
 
+// Back to the caller's pattern order (count path): stable radix sort of (pattern index -> count) pairs; the
+// indices are a permutation of 0..n-1, so the sorted values ARE the counts in the caller's order.
 template <class P, int NPL, int VBITS>
-static int run_locate(svfm_session* s, uint64_t n, const void* d_sp, const uint64_t* d_out_offs, uint64_t total,
-                      void* d_positions) {
+static int run_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) {
+    int rc;
+    if ((rc = s->rec_key_alt.reserve(n * 4))) return rc;
+    size_t temp = 0;
+    const int end_bit = bits_for(n) < 1 ? 1 : bits_for(n);
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp, idx, (uint32_t*)s->rec_key_alt.ptr, (const P*)d_cnt_work,
+                                              (P*)d_counts_out, (int64_t)n, 0, end_bit, s->stream));
+    if ((rc = s->cub_temp.reserve(temp))) return rc;
+    PhaseTimer pt(s, SVFM_PHASE_OTHER, 1 + (end_bit + 7) / 8);
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, idx, (uint32_t*)s->rec_key_alt.ptr, (const P*)d_cnt_work,
+                                              (P*)d_counts_out, (int64_t)n, 0, end_bit, s->stream));
+    return SVFM_OK;
+}
+
+// LF-walk + sampled-SA lookup for every SA row of every pattern (SVFM_PHASE_LOCATE).
+template <class P, int NPL, int VBITS>
+static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
+                      const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
     if (total == 0) return SVFM_OK;
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const uint64_t blocks = (total + LOCATE_THREADS - 1) / LOCATE_THREADS;
+    HeavyList<P> heavy{nullptr, nullptr, nullptr, nullptr, s->d_counters + 1, 0};
+    int rc;
+    if (heavy_seen) {
+        if ((rc = s->heavy_sp.reserve(heavy_seen * sizeof(P))) || (rc = s->heavy_cnt.reserve((heavy_seen + 1) * sizeof(P))) ||
+            (rc = s->heavy_obase.reserve(heavy_seen * sizeof(uint64_t))) || (rc = s->heavy_pat.reserve(heavy_seen * 4)) ||
+            (rc = s->heavy_offs.reserve((heavy_seen + 1) * sizeof(uint64_t))))
+            return rc;
+        heavy.sp = (P*)s->heavy_sp.ptr;
+        heavy.cnt = (P*)s->heavy_cnt.ptr;
+        heavy.obase = (uint64_t*)s->heavy_obase.ptr;
+        heavy.pat = (uint32_t*)s->heavy_pat.ptr;
+        heavy.capacity = heavy_seen;
+    }
+    {
+        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS>, n, LOCATE_THREADS, s->ix->device);
+        locate_warp_kernel<P, NPL, VBITS><<<grid, LOCATE_THREADS, 0, s->stream>>>(
+            dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+        SVFM_CUDA(cudaGetLastError());
+    }
+    if (!heavy_seen) return SVFM_OK;
+    // patterns with more than HEAVY_ROWS rows: one thread per row
+    if ((rc = run_scan<P, NPL, VBITS>(s, heavy_seen, heavy.cnt, (uint64_t*)s->heavy_offs.ptr))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[2], (uint64_t*)s->heavy_offs.ptr + heavy_seen, sizeof(uint64_t),
+                              cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    const uint64_t heavy_total = s->h_pinned[2];
+    const uint64_t blocks = (heavy_total + LOCATE_THREADS - 1) / LOCATE_THREADS;
     if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
-    locate_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
-        dix, (const P*)d_sp, d_out_offs, n, total, (P*)d_positions);
-    g_launches++;
-    SVFM_CUDA(cudaGetLastError());
+    if (blocks) {
+        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        locate_rows_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
+            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
+            (P*)d_positions, d_rec_key);
+        SVFM_CUDA(cudaGetLastError());
+    }
     return SVFM_OK;
 }
 
+struct MinOp {
+    __host__ __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a < b ? a : b; }
+};
+
+// Records (pattern index, position) -> the caller's CSR order.  Optional first stage (SVFM_SORTED): stable
+// sort by position, so that positions end up ascending inside every pattern.  Second stage: stable sort by
+// pattern index (LSD radix sort keeps SA-row order, or the ascending order of stage one, inside a pattern).
+// With want_offs the CSR offsets are rebuilt from the sorted pattern indices (run starts + reverse running
+// minimum); in direct mode they already exist.
 template <class P, int NPL, int VBITS>
-static int run_sort_segments(svfm_session* s, uint64_t n, const uint64_t* d_out_offs, uint64_t total,
-                             void** d_positions_inout) {
-    // SVFM_SORTED: ascending positions inside every pattern's segment (the reference returns SA-row order;
-    // its tests sort before comparing, get_accurate_result/mod.rs:53-56).
-    if (total == 0 || n == 0) return SVFM_OK;
-    if (total > 0x7fffffffull || n > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
-    int rc = s->positions_alt.reserve(total * sizeof(P));
-    if (rc) return rc;
-    cub::DoubleBuffer<P> keys((P*)*d_positions_inout, (P*)s->positions_alt.ptr);
-    size_t temp = 0;
-    SVFM_CUDA(cub::DeviceSegmentedSort::SortKeys(nullptr, temp, keys, (int)total, (int)n, d_out_offs, d_out_offs + 1, s->stream));
-    rc = s->cub_temp.reserve(temp);
-    if (rc) return rc;
-    SVFM_CUDA(cub::DeviceSegmentedSort::SortKeys(s->cub_temp.ptr, temp, keys, (int)total, (int)n, d_out_offs, d_out_offs + 1, s->stream));
-    g_launches += 3;
-    if (keys.Current() != (P*)*d_positions_inout) {
-        std::swap(s->positions, s->positions_alt);
+static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, bool by_position, bool want_offs,
+                                uint64_t* d_out_offs, void** d_positions_inout) {
+    int rc;
+    if (total > 0) {
+        if ((rc = s->positions_alt.reserve((total + 1) * sizeof(P))) || (rc = s->rec_key_alt.reserve((total + 1) * 4))) return rc;
+        cub::DoubleBuffer<uint32_t> pat((uint32_t*)s->rec_key.ptr, (uint32_t*)s->rec_key_alt.ptr);
+        cub::DoubleBuffer<P> pos((P*)s->positions.ptr, (P*)s->positions_alt.ptr);
+        const int pos_bits = bits_for(s->ix->text_len + 1) < 1 ? 1 : bits_for(s->ix->text_len + 1);
+        const int pat_bits = bits_for(n) < 1 ? 1 : bits_for(n);
+        size_t t1 = 0, t2 = 0;
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, pos, pat, (int64_t)total, 0, pos_bits, s->stream));
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, pat, pos, (int64_t)total, 0, pat_bits, s->stream));
+        if ((rc = s->cub_temp.reserve(t1 > t2 ? t1 : t2))) return rc;
+        if (by_position) {
+            PhaseTimer pt(s, SVFM_PHASE_SEGSORT, 1 + (pos_bits + 7) / 8);
+            SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, pos, pat, (int64_t)total, 0, pos_bits, s->stream));
+        }
+        {
+            PhaseTimer pt(s, SVFM_PHASE_OTHER, 1 + (pat_bits + 7) / 8);
+            SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t2, pat, pos, (int64_t)total, 0, pat_bits, s->stream));
+        }
+        if (pos.Current() != (P*)s->positions.ptr) std::swap(s->positions, s->positions_alt);
+        if (pat.Current() != (uint32_t*)s->rec_key.ptr) std::swap(s->rec_key, s->rec_key_alt);
         *d_positions_inout = s->positions.ptr;
     }
+    if (!want_offs) return SVFM_OK;
+    if ((rc = s->first.reserve((n + 1) * 8))) return rc;
+    uint64_t* first = (uint64_t*)s->first.ptr;
+    auto rin = thrust::make_reverse_iterator(first + n + 1);
+    auto rout = thrust::make_reverse_iterator(d_out_offs + n + 1);
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceScan::InclusiveScan(nullptr, temp, rin, rout, MinOp(), (int64_t)(n + 1), s->stream));
+    if ((rc = s->cub_temp.reserve(temp))) return rc;
+    PhaseTimer pt(s, SVFM_PHASE_OTHER, 4);
+    SVFM_CUDA(cudaMemsetAsync(first, 0xff, n * 8, s->stream));
+    s->h_pinned[4] = total;
+    SVFM_CUDA(cudaMemcpyAsync(first + n, &s->h_pinned[4], 8, cudaMemcpyHostToDevice, s->stream));  // first[n] = total
+    if (total)
+        run_starts_kernel<<<grid_for(total, 256, s->ix->device), 256, 0, s->stream>>>((const uint32_t*)s->rec_key.ptr, total, first);
+    SVFM_CUDA(cudaGetLastError());
+    SVFM_CUDA(cub::DeviceScan::InclusiveScan(s->cub_temp.ptr, temp, rin, rout, MinOp(), (int64_t)(n + 1), s->stream));
     return SVFM_OK;
 }
 
@@ -296,10 +523,11 @@ static int run_sort_segments(svfm_session* s, uint64_t n, const uint64_t* d_out_
         else { SVFM_DISPATCH_V(uint64_t, FN, __VA_ARGS__) }                 \
     } while (0)
 
-static int dispatch_search(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) { SVFM_DISPATCH(run_search, s, pb, d_sp, d_cnt); }
+static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work); }
 static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
-static int dispatch_locate(svfm_session* s, uint64_t n, const void* d_sp, const uint64_t* d_out_offs, uint64_t total, void* d_positions) { SVFM_DISPATCH(run_locate, s, n, d_sp, d_out_offs, total, d_positions); }
-static int dispatch_sort(svfm_session* s, uint64_t n, const uint64_t* d_out_offs, uint64_t total, void** d_positions) { SVFM_DISPATCH(run_sort_segments, s, n, d_out_offs, total, d_positions); }
+static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) { SVFM_DISPATCH(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out); }
+static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) { SVFM_DISPATCH(run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key); }
+static int dispatch_sortback_records(svfm_session* s, uint64_t n, uint64_t total, bool by_position, bool want_offs, uint64_t* d_out_offs, void** d_positions) { SVFM_DISPATCH(run_sortback_records, s, n, total, by_position, want_offs, d_out_offs, d_positions); }
 
 static int err_from_bits(int bits) {
     if (bits & ERRBIT_EMPTY_PATTERN) return SVFM_ERR_EMPTY_PATTERN;
@@ -307,34 +535,64 @@ static int err_from_bits(int bits) {
     return SVFM_OK;
 }
 
-// Device-resident count: search kernel only.  Leaves the error bits in s->d_err (checked by the caller).
-static int count_device(svfm_session* s, const PatternBatch& pb, void* d_sp, void* d_cnt) {
+// Device-resident count: small batches run the search kernel in the caller's order; large ones are
+// locality-sorted first and the counts are sorted back.  Leaves the error bits in s->d_err.
+static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_out) {
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
+    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
     if (pb.n == 0) return SVFM_OK;
-    return dispatch_search(s, pb, d_sp, d_cnt);
+    const SortPlan plan = plan_sort(s->ix, pb.n);
+    if (!plan.sorted) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
+    const uint64_t P = s->ix->type.pos_bits / 8;
+    const uint64_t* keys = nullptr;
+    const uint32_t* idx = nullptr;
+    int rc;
+    if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
+    if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
+    if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) return rc;
+    return dispatch_sortback_counts(s, pb.n, idx, s->cnt.ptr, d_counts_out);
 }
 
-// Device-resident locate pipeline: search -> scan -> (sync for the total) -> LF-walk -> optional sort.
+// Device-resident locate pipeline.
+//   small batch : search -> scan -> (sync: total) -> LF-walk straight into CSR order [-> sort by position]
+//   large batch : locality sort -> search -> scan (work order) -> (sync: total) -> LF-walk into records
+//                 (pattern index, position) [-> sort by position] -> stable sort by pattern index -> CSR offsets
 static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags, uint64_t* d_out_offs,
                          void** d_positions, uint64_t* total_out) {
     const uint64_t P = s->ix->type.pos_bits / 8;
     int rc;
+    SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
+    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
     if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
-    if ((rc = count_device(s, pb, s->sp.ptr, s->cnt.ptr))) return rc;
-    if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, d_out_offs))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], d_out_offs + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    const SortPlan plan = plan_sort(s->ix, pb.n);
+    const uint64_t* keys = nullptr;
+    const uint32_t* idx = nullptr;
+    uint64_t* offs_work = d_out_offs;  // small batch: work order == caller order
+    if (plan.sorted) {
+        if ((rc = s->woffs.reserve((pb.n + 1) * 8))) return rc;
+        if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
+        offs_work = (uint64_t*)s->woffs.ptr;
+    }
+    if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) return rc;
+    if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], offs_work + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[3], s->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaStreamSynchronize(s->stream));
     if ((rc = err_from_bits((int)(s->h_pinned[1] & 0xffffffffu)))) return rc;
     const uint64_t total = s->h_pinned[0];
+    const uint64_t heavy_seen = s->h_pinned[3];
     *total_out = total;
     if ((rc = s->positions.reserve((total + 1) * P))) return rc;
+    const bool by_position = (flags & SVFM_SORTED) != 0;
+    const bool records = plan.sorted || by_position;
+    if (records && (rc = s->rec_key.reserve((total + 1) * 4))) return rc;
     *d_positions = s->positions.ptr;
-    if ((rc = dispatch_locate(s, pb.n, s->sp.ptr, d_out_offs, total, s->positions.ptr))) return rc;
-    if (flags & SVFM_SORTED) {
-        if ((rc = dispatch_sort(s, pb.n, d_out_offs, total, d_positions))) return rc;
-    }
+    if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, offs_work, total, heavy_seen, s->positions.ptr,
+                              records ? (uint32_t*)s->rec_key.ptr : nullptr)))
+        return rc;
+    if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, plan.sorted, d_out_offs, d_positions))) return rc;
     return SVFM_OK;
 }
 
@@ -465,9 +723,9 @@ int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, 
     const uint64_t P = ix->type.pos_bits / 8;
     PatternBatch pb;
     if ((rc = upload_patterns(s, pats, offs, n, fixed_len, flags, pb))) return rc;
-    if ((rc = s->cnt.reserve(n * P))) return rc;
-    if ((rc = count_device(s, pb, nullptr, s->cnt.ptr))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(counts_out, s->cnt.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
+    if ((rc = s->counts_out.reserve(n * P))) return rc;  // not s->cnt: count_device uses that in work order
+    if ((rc = count_device(s, pb, s->counts_out.ptr))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(counts_out, s->counts_out.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaStreamSynchronize(s->stream));
     return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
@@ -566,13 +824,31 @@ int svfm_session_sync(svfm_session* s) {
 
 void* svfm_session_stream(svfm_session* s) { return s ? (void*)s->stream : nullptr; }
 
+int svfm_session_set_timing(svfm_session* s, int enabled) {
+    if (!s) return SVFM_ERR_BAD_ARG;
+    s->timing = enabled != 0;
+    return SVFM_OK;
+}
+
+int svfm_session_get_timing(svfm_session* s, double ms[SVFM_PHASE_MAX], uint64_t launches[SVFM_PHASE_MAX], int reset) {
+    if (!s) return SVFM_ERR_BAD_ARG;
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    collect_spans(s);
+    for (int i = 0; i < SVFM_PHASE_MAX; i++) {
+        if (ms) ms[i] = s->phase_ms[i];
+        if (launches) launches[i] = s->phase_launches[i];
+        if (reset) { s->phase_ms[i] = 0; s->phase_launches[i] = 0; }
+    }
+    return SVFM_OK;
+}
+
 int svfm_count_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
                             uint32_t fixed_len, uint32_t flags, void* d_counts_out) {
     if (!s || (n && (!d_pats || !d_counts_out))) return SVFM_ERR_BAD_ARG;
     if (!d_offs && fixed_len == 0 && n) return SVFM_ERR_EMPTY_PATTERN;
     SVFM_CUDA(cudaSetDevice(s->ix->device));
     PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
-    int rc = count_device(s, pb, nullptr, d_counts_out);
+    int rc = count_device(s, pb, d_counts_out);
     if (rc) return rc;
     // the error word is read back asynchronously; svfm_session_sync + the next call report it
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -603,6 +879,13 @@ void* svfm_host_alloc(size_t bytes) {
 
 void svfm_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int svfm_set_tuning(int key, uint64_t value) {
+    switch (key) {
+        case SVFM_TUNE_SORT_MIN: g_sort_min.store(value); return SVFM_OK;
+        default: return SVFM_ERR_BAD_ARG;
+    }
 }
 
 const char* svfm_last_error(void) { return g_last_error.c_str(); }

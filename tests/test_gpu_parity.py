@@ -14,12 +14,16 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "readme_example.json")
 
 
-@pytest.fixture(scope="module")
-def fm():
+@pytest.fixture(scope="module", params=["sort_always", "sort_never", "sort_default"])
+def fm(request):
+    """Every parity test runs with the locality sort forced on, forced off and at its default threshold:
+    results must not depend on it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
-    _ffi.lib()
-    return fm
+    value = {"sort_always": 0, "sort_never": 2**64 - 1, "sort_default": 1 << 17}[request.param]
+    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, value) == 0
+    yield fm
+    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
@@ -149,6 +153,10 @@ def test_edge_cases(oracle, fm, vec_bits):
     ora, gpu, _, _ = _pair(oracle, fm, b"A" * 777, [b"A", b"C", b"G", b"T"], 64, 2, vec_bits, 2, 3)
     _check_batch(ora, gpu, [b"AAAA", b"A", b"C", b"AC", b"A" * 777, b"A" * 778])
     assert gpu.count(b"AAAA") == 774
+    # more than HEAVY_ROWS (1024) rows per pattern: the row-parallel locate kernel, mixed with light patterns
+    text = b"A" * 3000 + b"CGT" * 700 + b"A" * 2500
+    ora_h, gpu_h, _, _ = _pair(oracle, fm, text, [b"A", b"C", b"G", b"T"], 32, 2, vec_bits, 2, 4)
+    _check_batch(ora_h, gpu_h, [b"A", b"AA", b"CGT", b"GTC", b"T", b"AAAAAAAAAAAAAAAAAAAAAAAA", b"TA", b"CC", b"ACGT"] * 5)
     # empty pattern: reference panics (count_array.rs:211) -> error code, nothing computed
     with pytest.raises(fm.EmptyPattern):
         gpu.count(b"")
