@@ -30,17 +30,12 @@ struct DevIndex {
 };
 
 // ---- loads --------------------------------------------------------------------------------------
-// Random gathers with no reuse inside a CTA: read-only path, do not allocate in L1 so that the small
-// tables (encoding table, count array, kLTS) stay resident.
-__device__ __forceinline__ uint32_t ld_gather_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
+// Index gathers go through the read-only path and allocate in L1: the planes of one block are fetched by
+// separate instructions that hit the same 1-2 sectors, and neighbouring lanes/warps of a locality-sorted
+// batch share sectors (ncu, round 1: without L1 allocation every plane load was a separate L2 request).
+__device__ __forceinline__ uint32_t ld_gather_u32(const uint32_t* p) { return __ldg(p); }
 __device__ __forceinline__ uint64_t ld_gather_u64(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
+    return __ldg(reinterpret_cast<const unsigned long long*>(p));
 }
 template <class P> __device__ __forceinline__ P ld_gather(const P* p);
 template <> __device__ __forceinline__ uint32_t ld_gather<uint32_t>(const uint32_t* p) { return ld_gather_u32(p); }

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -140,6 +142,10 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
         blob_len, t, L, err_detail);
     if (rc) return rc;
     SVFM_CUDA(cudaSetDevice(device));
+    // Sparse 32-byte gathers dominate: ask L2 to fetch single sectors instead of 64-byte pairs (ncu, round 1:
+    // with the default granularity half of the DRAM sectors read by the search kernel were never requested).
+    (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    (void)cudaGetLastError();
     svfm_index* ix = new svfm_index();
     ix->type = t;
     ix->L = L;
@@ -262,15 +268,17 @@ struct SessionLease {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch over the 30 (P, BlockN, Vector) instantiations
 // ---------------------------------------------------------------------------------------------
-// Grid for a grid-stride kernel: exactly the CTAs that can be resident at once (SMs x occupancy), so that
-// there is no partial second wave; fewer when the work does not fill the machine.
+// Grid for a grid-stride kernel: a multiple of the CTAs that can be resident at once (SMs x occupancy);
+// fewer when the work does not fill the machine.  Measured on B200 (1 Gbp index, 100M patterns): 4 resident
+// waves run the search kernel 13% faster than exactly one (shorter per-thread item chains, less tail).
 template <class K>
 static int resident_grid(K kernel, uint64_t work_items, int threads, int device) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     uint64_t blocks = (work_items + threads - 1) / threads;
-    const uint64_t cap = (uint64_t)sms * per_sm;
+    static const double mult = [] { const char* e = std::getenv("SVFM_GRID_MULT"); return e ? atof(e) : 4.0; }();
+    const uint64_t cap = (uint64_t)((double)sms * per_sm * mult);
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     return (int)blocks;
@@ -614,26 +622,212 @@ static int check_host_patterns(const uint8_t* pats, const uint64_t* offs, uint64
     return SVFM_OK;
 }
 
-static int upload_patterns(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                           uint32_t flags, PatternBatch& pb) {
+// ---------------------------------------------------------------------------------------------
+// Host-buffer entry points.  A large batch is cut into chunks that flow through up to HOST_WORKERS
+// sessions (one CUDA stream each, driven by one host thread each), so that the upload of chunk i+1, the
+// kernels of chunk i and the download of chunk i-1 overlap on the copy engines and the SMs.
+// ---------------------------------------------------------------------------------------------
+static std::atomic<uint64_t> g_chunk_patterns{[] {
+    const char* e = std::getenv("SVFM_CHUNK");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(16u << 20);
+}()};
+constexpr int HOST_WORKERS = 3;
+
+__global__ void add_base_kernel(uint64_t* __restrict__ v, uint64_t n, uint64_t base) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] += base;
+}
+
+struct ChunkPlan {
+    uint64_t n = 0, chunk = 0, chunks = 0;
+    uint64_t begin(uint64_t c) const { return c * chunk; }
+    uint64_t end(uint64_t c) const { return (c + 1) * chunk < n ? (c + 1) * chunk : n; }
+};
+
+static ChunkPlan plan_chunks(uint64_t n) {
+    ChunkPlan p;
+    p.n = n;
+    uint64_t c = g_chunk_patterns.load();
+    if (c == 0) c = n;
+    p.chunks = (n + c - 1) / c;
+    if (p.chunks == 0) p.chunks = 1;
+    p.chunk = (n + p.chunks - 1) / p.chunks;  // even chunks
+    if (p.chunk == 0) p.chunk = 1;
+    p.chunks = (n + p.chunk - 1) / p.chunk;
+    if (p.chunks == 0) p.chunks = 1;
+    return p;
+}
+
+// Upload patterns [a, b) of a host batch into the session's arena.
+static int upload_chunk(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t a, uint64_t b,
+                        uint32_t fixed_len, uint32_t flags, PatternBatch& pb) {
+    int rc;
+    pb.n = b - a;
+    pb.fixed_len = fixed_len;
+    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.offs = nullptr;
+    if (!offs) {
+        const uint64_t bytes = (b - a) * (uint64_t)fixed_len;
+        if ((rc = s->pats.reserve(bytes + 16))) return rc;
+        SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + a * (uint64_t)fixed_len, bytes, cudaMemcpyHostToDevice, s->stream));
+        pb.pats = (const uint8_t*)s->pats.ptr;
+        return SVFM_OK;
+    }
+    const uint64_t base = offs[a], bytes = offs[b] - base;
+    if ((rc = s->pats.reserve(bytes + 16))) return rc;
+    if ((rc = s->offs.reserve((b - a + 1) * sizeof(uint64_t)))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + base, bytes, cudaMemcpyHostToDevice, s->stream));
+    SVFM_CUDA(cudaMemcpyAsync(s->offs.ptr, offs + a, (b - a + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    pb.pats = (const uint8_t*)s->pats.ptr - base;  // offsets stay absolute
+    pb.offs = (const uint64_t*)s->offs.ptr;
+    return SVFM_OK;
+}
+
+template <class Fn>
+static int run_workers(svfm_index* ix, uint64_t chunks, Fn&& per_chunk) {
+    const int workers = (int)(chunks < (uint64_t)HOST_WORKERS ? chunks : (uint64_t)HOST_WORKERS);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> first_err{SVFM_OK};
+    std::string err_text;
+    std::mutex err_mu;
+    auto body = [&]() {
+        SessionLease lease(ix);
+        int rc = lease.acquire();
+        for (;;) {
+            const uint64_t c = next.fetch_add(1);
+            if (c >= chunks) break;
+            const bool run = (rc == SVFM_OK && first_err.load() == SVFM_OK);
+            if (run) rc = per_chunk(lease.s, c);
+            if (rc != SVFM_OK) {
+                int expected = SVFM_OK;
+                if (first_err.compare_exchange_strong(expected, rc)) {
+                    std::lock_guard<std::mutex> g(err_mu);
+                    err_text = g_last_error;
+                }
+            }
+            if (!run || rc != SVFM_OK) per_chunk(nullptr, c);  // publish "nothing": nobody may wait on this chunk forever
+        }
+        if (lease.s) cudaStreamSynchronize(lease.s->stream);
+    };
+    if (workers <= 1) {
+        body();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < workers; t++) th.emplace_back(body);
+        body();
+        for (auto& t : th) t.join();
+    }
+    if (first_err.load() != SVFM_OK) g_last_error = err_text;
+    return first_err.load();
+}
+
+static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                      uint32_t flags, void* counts_out) {
+    const uint64_t P = ix->type.pos_bits / 8;
+    const ChunkPlan cp = plan_chunks(n);
+    return run_workers(ix, cp.chunks, [&](svfm_session* s, uint64_t c) -> int {
+        if (!s) return SVFM_OK;
+        const uint64_t a = cp.begin(c), b = cp.end(c);
+        PatternBatch pb;
+        int rc;
+        if ((rc = upload_chunk(s, pats, offs, a, b, fixed_len, flags, pb))) return rc;
+        if ((rc = s->counts_out.reserve((b - a) * P))) return rc;  // not s->cnt: count_device uses that in work order
+        if ((rc = count_device(s, pb, s->counts_out.ptr))) return rc;
+        SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
+    });
+}
+
+static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
+                       uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, void** alloc_out,
+                       uint64_t* total_out) {
+    if (!ix || !out_offs || !total_out) return SVFM_ERR_BAD_ARG;
+    *total_out = 0;
+    if (alloc_out) *alloc_out = nullptr;
     uint64_t bytes = 0;
     int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
     if (rc) return rc;
-    pb.n = n;
-    pb.fixed_len = fixed_len;
-    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
-    pb.pats = nullptr;
-    pb.offs = nullptr;
+    out_offs[0] = 0;
     if (n == 0) return SVFM_OK;
-    const uint64_t base = offs ? offs[0] : 0;
-    if ((rc = s->pats.reserve(bytes - base + 16))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + base, bytes - base, cudaMemcpyHostToDevice, s->stream));
-    pb.pats = (const uint8_t*)s->pats.ptr - base;  // offsets stay absolute
-    if (offs) {
-        if ((rc = s->offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
-        SVFM_CUDA(cudaMemcpyAsync(s->offs.ptr, offs, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
-        pb.offs = (const uint64_t*)s->offs.ptr;
+    const uint64_t P = ix->type.pos_bits / 8;
+    const ChunkPlan cp = plan_chunks(n);
+    // chunk totals are published in completion order; a chunk's output base is the sum of all earlier totals
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t> totals(cp.chunks, 0);
+    std::vector<char> known(cp.chunks, 0);
+    std::vector<void*> chunk_bufs(alloc_out ? cp.chunks : 0, nullptr);  // alloc mode: per-chunk pinned staging
+    std::atomic<bool> overflow{false};
+    auto publish = [&](uint64_t c, uint64_t t) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!known[c]) { totals[c] = t; known[c] = 1; }
+        cv.notify_all();
+    };
+    rc = run_workers(ix, cp.chunks, [&](svfm_session* s, uint64_t c) -> int {
+        if (!s) { publish(c, 0); return SVFM_OK; }
+        const uint64_t a = cp.begin(c), b = cp.end(c), m = b - a;
+        PatternBatch pb;
+        int r;
+        if ((r = upload_chunk(s, pats, offs, a, b, fixed_len, flags, pb))) return r;
+        if ((r = s->out_offs.reserve((m + 1) * sizeof(uint64_t)))) return r;
+        void* d_positions = nullptr;
+        uint64_t total = 0;
+        if ((r = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return r;
+        publish(c, total);
+        uint64_t base = 0;
+        {
+            std::unique_lock<std::mutex> g(mu);
+            cv.wait(g, [&] { for (uint64_t j = 0; j < c; j++) if (!known[j]) return false; return true; });
+            for (uint64_t j = 0; j < c; j++) base += totals[j];
+        }
+        const bool last = (c + 1 == cp.chunks);
+        const uint64_t n_offs = m + (last ? 1 : 0);
+        if (base) {
+            add_base_kernel<<<grid_for(n_offs, 256, ix->device), 256, 0, s->stream>>>((uint64_t*)s->out_offs.ptr, n_offs, base);
+            g_launches++;
+            SVFM_CUDA(cudaGetLastError());
+        }
+        SVFM_CUDA(cudaMemcpyAsync(out_offs + a, s->out_offs.ptr, n_offs * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        if (total) {
+            if (alloc_out) {
+                void* buf = nullptr;
+                cudaError_t e = cudaHostAlloc(&buf, total * P, cudaHostAllocDefault);
+                if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); g_last_error = cudaGetErrorString(e); return SVFM_ERR_NOMEM; }
+                chunk_bufs[c] = buf;
+                SVFM_CUDA(cudaMemcpyAsync(buf, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
+            } else if (base + total <= capacity) {
+                SVFM_CUDA(cudaMemcpyAsync((uint8_t*)positions + base * P, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
+            } else {
+                overflow.store(true);
+            }
+        }
+        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        return SVFM_OK;
+    });
+    uint64_t total = 0;
+    for (uint64_t c = 0; c < cp.chunks; c++) total += totals[c];
+    *total_out = total;
+    if (alloc_out) {
+        if (rc == SVFM_OK && total) {
+            void* dst = nullptr;
+            if (cp.chunks == 1) {
+                dst = chunk_bufs[0];
+                chunk_bufs[0] = nullptr;
+            } else {
+                if (cudaHostAlloc(&dst, total * P, cudaHostAllocDefault) != cudaSuccess) { rc = SVFM_ERR_NOMEM; dst = nullptr; }
+                uint64_t at = 0;
+                for (uint64_t c = 0; dst && c < cp.chunks; c++) {
+                    if (totals[c]) std::memcpy((uint8_t*)dst + at * P, chunk_bufs[c], totals[c] * P);
+                    at += totals[c];
+                }
+            }
+            *alloc_out = dst;
+        }
+        for (void* b : chunk_bufs) if (b) cudaFreeHost(b);
     }
+    if (rc) return rc;
+    if (overflow.load() || (!alloc_out && total > capacity)) return SVFM_ERR_CAPACITY;
     return SVFM_OK;
 }
 
@@ -717,57 +911,7 @@ int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, 
     int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
     if (rc) return rc;
     if (n == 0) return SVFM_OK;
-    SessionLease lease(ix);
-    if ((rc = lease.acquire())) return rc;
-    svfm_session* s = lease.s;
-    const uint64_t P = ix->type.pos_bits / 8;
-    PatternBatch pb;
-    if ((rc = upload_patterns(s, pats, offs, n, fixed_len, flags, pb))) return rc;
-    if ((rc = s->counts_out.reserve(n * P))) return rc;  // not s->cnt: count_device uses that in work order
-    if ((rc = count_device(s, pb, s->counts_out.ptr))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(counts_out, s->counts_out.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
-    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    SVFM_CUDA(cudaStreamSynchronize(s->stream));
-    return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
-}
-
-static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                       uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, void** alloc_out,
-                       uint64_t* total_out) {
-    if (!ix || !out_offs || !total_out) return SVFM_ERR_BAD_ARG;
-    *total_out = 0;
-    if (alloc_out) *alloc_out = nullptr;
-    uint64_t bytes = 0;
-    int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
-    if (rc) return rc;
-    out_offs[0] = 0;
-    if (n == 0) return SVFM_OK;
-    SessionLease lease(ix);
-    if ((rc = lease.acquire())) return rc;
-    svfm_session* s = lease.s;
-    const uint64_t P = ix->type.pos_bits / 8;
-    PatternBatch pb;
-    if ((rc = upload_patterns(s, pats, offs, n, fixed_len, flags, pb))) return rc;
-    if ((rc = s->out_offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
-    void* d_positions = nullptr;
-    uint64_t total = 0;
-    if ((rc = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return rc;
-    *total_out = total;
-    SVFM_CUDA(cudaMemcpyAsync(out_offs, s->out_offs.ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-    void* dst = positions;
-    if (alloc_out) {
-        if (total) {
-            cudaError_t e = cudaHostAlloc(&dst, total * P, cudaHostAllocDefault);
-            if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); g_last_error = cudaGetErrorString(e); return SVFM_ERR_NOMEM; }
-        } else dst = nullptr;
-        *alloc_out = dst;
-    } else if (total > capacity) {
-        SVFM_CUDA(cudaStreamSynchronize(s->stream));
-        return SVFM_ERR_CAPACITY;
-    }
-    if (total) SVFM_CUDA(cudaMemcpyAsync(dst, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
-    SVFM_CUDA(cudaStreamSynchronize(s->stream));
-    return SVFM_OK;
+    return count_host(ix, pats, offs, n, fixed_len, flags, counts_out);
 }
 
 int svfm_locate_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
@@ -884,6 +1028,7 @@ void svfm_host_free(void* p) {
 int svfm_set_tuning(int key, uint64_t value) {
     switch (key) {
         case SVFM_TUNE_SORT_MIN: g_sort_min.store(value); return SVFM_OK;
+        case SVFM_TUNE_CHUNK: g_chunk_patterns.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -244,3 +244,58 @@ def test_medium_random_batch(oracle, fm):
         offs, pos = g2.locate_batch(pats)
         assert np.array_equal(offs, oo) and np.array_equal(pos, op_)
         assert np.array_equal(g2.count_batch(pats).astype(np.uint64), oc)
+
+
+def test_chunked_host_pipeline(oracle, fm):
+    """The host-buffer entry points cut big batches into chunks that flow through several streams / host
+    threads: results (CSR offsets with per-chunk bases, positions, counts, capacity handling) must not change."""
+    import ctypes as C
+    from sview_fmindex_b200 import _ffi
+    po = oracle
+    L = _ffi.lib()
+    rng = np.random.default_rng(99)
+    n = 400_000
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)]
+    table, sc = po.encoding_table([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
+    t = po.IndexType(32, 3, 64, True)
+    blob = po.build_blob(t, text, sc, table, 3, 2)
+    ora = po.OracleFmIndex.load(blob, t)
+    gpu = fm.FmIndex.load(blob, fm.IndexType(32, 3, 64, True))
+    m = 50_000
+    starts = rng.integers(0, n - 8, size=m)
+    pats = text[starts[:, None] + np.arange(8)[None, :]].copy()
+    pats[::5, 2] = ord("N")
+    oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
+    var = [bytes(p[: 3 + (i % 6)]) for i, p in enumerate(pats[:20_000])]
+    vo, vp = None, None
+    try:
+        for chunk in (777, 4096, 25_000, 0):
+            assert L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, chunk) == 0
+            assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc)
+            offs, pos = gpu.locate_batch(pats)
+            assert np.array_equal(offs, oo) and np.array_equal(pos, op_), chunk
+            offs_s, pos_s = gpu.locate_batch(pats, sorted_=True)
+            idx = np.repeat(np.arange(m, dtype=np.uint64), np.diff(oo).astype(np.int64))
+            assert np.array_equal(offs_s, oo) and np.array_equal(pos_s, op_[np.lexsort((op_, idx))])
+            # variable-length patterns through the offsets path
+            o2, p2 = gpu.locate_batch(var)
+            if vo is None:
+                vo, vp = o2, p2
+                for i in (0, 1, 7, 19_999):
+                    assert np.array_equal(p2[int(o2[i]):int(o2[i + 1])].astype(np.uint64), ora.locate(var[i]))
+            assert np.array_equal(o2, vo) and np.array_equal(p2, vp)
+            # caller-provided buffer: exact capacity works, one short reports SVFM_ERR_CAPACITY + the needed total
+            total = int(oo[-1])
+            flat = np.ascontiguousarray(pats).reshape(-1)
+            out_offs = np.zeros(m + 1, dtype=np.uint64)
+            out_pos = np.zeros(total, dtype=np.uint32)
+            tot = C.c_uint64()
+            rc = L.svfm_locate_batch(gpu.handle, flat.ctypes.data, None, m, 8, 0, out_offs.ctypes.data, out_pos.ctypes.data, total, C.byref(tot))
+            assert rc == 0 and tot.value == total and np.array_equal(out_pos, op_) and np.array_equal(out_offs, oo)
+            rc = L.svfm_locate_batch(gpu.handle, flat.ctypes.data, None, m, 8, 0, out_offs.ctypes.data, out_pos.ctypes.data, total - 1, C.byref(tot))
+            assert rc == _ffi.SVFM_ERR_CAPACITY and tot.value == total and np.array_equal(out_offs, oo)
+            # an empty pattern in a late chunk fails the whole call before any work
+            with pytest.raises(fm.EmptyPattern):
+                gpu.locate_batch(var[:5000] + [b""] + var[5000:6000])
+    finally:
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 16 << 20)
