@@ -42,26 +42,23 @@ __global__ void synth_patterns_kernel(const uint8_t* text, uint64_t n, uint8_t* 
 }
 
 constexpr int GATHER_ILP = 8;
-__global__ void gather32_kernel(const uint4* __restrict__ buf, uint64_t sectors, uint64_t loads, uint64_t seed,
+__global__ void gather32_kernel(const uint8_t* __restrict__ buf, uint64_t sectors, uint64_t loads, uint64_t seed,
                                 unsigned long long* sink) {
-    // each thread issues GATHER_ILP independent 32-byte loads (2 x LDG.128 per sector) per trip
+    // each thread keeps GATHER_ILP independent loads in flight, one 8-byte load per uniformly random 32-byte
+    // sector (what one rank query reads of a checkpoint row); the sector is the unit of DRAM/L2 traffic
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t acc = 0;
+    uint64_t acc = 0;
     for (uint64_t base = tid * GATHER_ILP; base < loads; base += nthreads * GATHER_ILP) {
-        uint4 a[GATHER_ILP], b[GATHER_ILP];
+        uint64_t v[GATHER_ILP];
 #pragma unroll
         for (int u = 0; u < GATHER_ILP; u++) {
             // multiply-shift range reduction (a 64-bit modulo would make the kernel ALU-bound)
-            const uint64_t s = __umul64hi(hash_at(seed, base + u), sectors);
-            const uint4* p = buf + s * 2;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w) : "l"(p));
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(b[u].x), "=r"(b[u].y), "=r"(b[u].z), "=r"(b[u].w) : "l"(p + 1));
+            const uint64_t s = __umul64hi(splitmix64(seed + base + u), sectors);
+            v[u] = __ldg(reinterpret_cast<const unsigned long long*>(buf + s * 32));
         }
 #pragma unroll
-        for (int u = 0; u < GATHER_ILP; u++) acc ^= a[u].x ^ a[u].w ^ b[u].y ^ b[u].z;
+        for (int u = 0; u < GATHER_ILP; u++) acc ^= v[u];
     }
     if (acc == 0x12345679u) atomicAdd(sink, 1ull);
 }
@@ -157,7 +154,7 @@ int svfm_bench_gather32(const uint8_t* d_buf, uint64_t bytes, uint64_t loads, ui
     float best = 1e30f;
     for (uint32_t it = 0; it <= iters; it++) {
         SVFM_CUDA(cudaEventRecord(e0, st));
-        gather32_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(d_buf), sectors, loads, seed + it, d_sink);
+        gather32_kernel<<<148 * 16, 256, 0, st>>>(d_buf, sectors, loads, seed + it, d_sink);
         g_launches++;
         SVFM_CUDA(cudaEventRecord(e1, st));
         SVFM_CUDA(cudaEventSynchronize(e1));

@@ -1,0 +1,47 @@
+// Experiment: does cudaLimitMaxL2FetchGranularity change random 32-byte gather throughput on B200?
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ uint64_t mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+template <int ILP, int BYTES>
+__global__ void gather(const uint8_t* buf, uint64_t sectors, uint64_t loads, uint64_t seed, unsigned long long* sink) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t acc = 0;
+    for (uint64_t base = tid * ILP; base < loads; base += nth * ILP) {
+        uint64_t v[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            const uint64_t s = __umul64hi(mix(seed + base + u), sectors);
+            if (BYTES == 8) v[u] = __ldg((const unsigned long long*)(buf + s * 32));
+            else { uint4 q = __ldg((const uint4*)(buf + s * 32)); v[u] = q.x ^ q.w; }
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; u++) acc ^= v[u];
+    }
+    if (acc == 0x1234567) atomicAdd(sink, 1ull);
+}
+int main() {
+    const uint64_t bytes = 687ull << 20, loads = 1ull << 28;
+    uint8_t* buf; unsigned long long* sink;
+    cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes); cudaMalloc(&sink, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int gran : {0, 32, 64, 128}) {
+        if (gran) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); if (e) printf("set %d: %s\n", gran, cudaGetErrorString(e)); }
+        size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        for (int blocks : {148 * 8, 148 * 16}) {
+            float best8 = 1e9, best16 = 1e9;
+            for (int it = 0; it < 4; it++) {
+                float ms;
+                cudaEventRecord(e0); gather<8, 8><<<blocks, 256>>>(buf, bytes / 32, loads, it, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best8) best8 = ms;
+                cudaEventRecord(e0); gather<8, 16><<<blocks, 256>>>(buf, bytes / 32, loads, it, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best16) best16 = ms;
+            }
+            printf("gran set=%d got=%zu blocks=%d: 8B loads %.2f Gsect/s (%.2f ms)   16B loads %.2f Gsect/s\n", gran, got, blocks,
+                   loads / best8 / 1e6, best8, loads / best16 / 1e6);
+        }
+    }
+    return 0;
+}
