@@ -166,9 +166,10 @@ void svfm_host_free(void* p);
  * locality-sorted by their trailing symbols before the search (0 = always, UINT64_MAX = never; default
  * 131072, or the SVFM_SORT_MIN environment variable).  SVFM_TUNE_CHUNK: the host-buffer entry points cut a
  * batch into chunks of about this many patterns and pipeline upload / kernels / download over several
- * streams (0 = one chunk; default 16 Mi, or the SVFM_CHUNK environment variable).  Results never depend
- * on either. */
-enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1 };
+ * streams (0 = one chunk; default 16 Mi, or the SVFM_CHUNK environment variable).  SVFM_TUNE_TWO_PHASE_MIN:
+ * locality-sorted batches with at least this many patterns are re-sorted by SA position part-way through the
+ * backward search (default: never -- measured slower in round 1; or SVFM_TWO_PHASE_MIN).  Results never depend on any of them. */
+enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_TWO_PHASE_MIN = 2 };
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */
 uint64_t svfm_launch_count(void);     /* kernels launched by this library since process start */

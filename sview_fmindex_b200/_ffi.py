@@ -30,6 +30,7 @@ SVFM_ERR_CUDA = 30
 
 SVFM_TUNE_SORT_MIN = 0
 SVFM_TUNE_CHUNK = 1
+SVFM_TUNE_TWO_PHASE_MIN = 2
 SVFM_REVERSED = 1
 SVFM_SORTED = 2
 

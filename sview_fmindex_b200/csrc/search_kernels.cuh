@@ -86,15 +86,46 @@ pack_keys_kernel(const uint8_t* __restrict__ table, uint32_t S, const PatternBat
     if (errbits) atomicOr(err, errbits);
 }
 
+// State of a pattern between the two phases of a large batch (see SearchIO): moved as the VALUE of the
+// radix sort that re-orders the batch by its current SA position.
+template <class P>
+struct Item {
+    uint64_t key;   // packed trailing symbols (pack_keys_kernel)
+    uint32_t idx;   // the caller's pattern index
+    uint32_t pi;    // symbols still to consume (forward index of the next one + 1); 0 = finished
+    P cnt;          // ep - sp
+};
+
+template <class P>
+struct SearchIO {
+    const uint64_t* keys;   // packed keys in work order, or NULL (symbols come from the pattern bytes)
+    const uint32_t* idx;    // pattern index of each work item, or NULL (identity)
+    uint32_t bits;          // bits per symbol in the key
+    uint32_t max_steps;     // backward steps to run in this launch (0xffffffff = to the end)
+    const P* sp_in;         // resume: current sp of each work item (sorted ascending); NULL = start from the kLTS seed
+    const Item<P>* items_in;
+    P* sp_out;              // work order, nullable
+    P* cnt_out;             // work order, nullable
+    Item<P>* items_out;     // nullable: state for the next phase
+    uint32_t* idx_out;      // nullable: pattern index per work item (resume launches)
+    unsigned long long* heavy_seen;  // nullable
+    int* err;
+};
+
 // FmIndex::get_pos_range (locate/with_slice.rs:21-33) for one pattern per thread, grid-stride.
 // Work item w handles pattern idx[w] (idx == NULL: identity).  With keys != NULL the last 64/bits symbols of
-// the pattern come out of keys[w] (see pack_keys_kernel).  Outputs in WORK order, coalesced:
-// sp_work[w] (nullable) and cnt_work[w] = ep - sp.
-template <class P, int NPL, int VBITS>
+// the pattern come out of keys[w] (see pack_keys_kernel).  Outputs in WORK order, coalesced.
+//
+// Large batches run it twice.  Phase 1 (work order = locality sort by trailing symbols) runs the kLTS seed and
+// the first max_steps backward steps: neighbouring lanes share rows/blocks there.  Then the batch is radix-sorted
+// by the current sp, and phase 2 (RESUME) finishes the search in SA order: LF-mapping keeps the relative order
+// of rows inside a symbol class, so from then on the rows a window of neighbouring work items touches stay
+// confined to a few narrow, slowly advancing windows of the checkpoint/block arrays -- every line is fetched from
+// DRAM once per step instead of once per pattern (ncu, round 1: the single-phase kernel read 155 GB for 100 M
+// 20-mers because its last ~8 steps were random sector pairs with >= 64-byte line fills).
+template <class P, int NPL, int VBITS, bool RESUME>
 __global__ void __launch_bounds__(SEARCH_THREADS)
-search_kernel(const DevIndex<P> ix, const PatternBatch pb, const uint64_t* __restrict__ keys,
-              const uint32_t* __restrict__ idx, uint32_t bits, P* __restrict__ sp_work, P* __restrict__ cnt_work,
-              unsigned long long* __restrict__ heavy_seen, int* __restrict__ err) {
+search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io) {
     __shared__ uint8_t s_table[256];
     __shared__ P s_count[65];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = ix.table ? ix.table[i] : (uint8_t)i;
@@ -103,17 +134,29 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const uint64_t* __res
 
     const uint32_t S = ix.symbol_count;
     const uint32_t k = ix.kmer_size;
-    const uint32_t in_key = keys ? 64u / bits : 0u;  // symbols (from the end) available in the key
+    const uint32_t bits = io.bits;
+    const bool have_keys = RESUME || io.keys != nullptr;
+    const uint32_t in_key = have_keys ? 64u / bits : 0u;  // symbols (from the end) available in the key
     const uint64_t sym_mask = (1ull << bits) - 1;
     int errbits = 0;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < pb.n; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = idx ? (uint64_t)idx[w] : w;
-        const uint64_t key = keys ? keys[w] : 0ull;
+        uint64_t i, key, pi = 0;
+        P sp = 0, ep = 0;
+        if (RESUME) {
+            const Item<P> it = io.items_in[w];
+            i = it.idx;
+            key = it.key;
+            pi = it.pi;
+            sp = io.sp_in[w];
+            ep = (P)(sp + it.cnt);
+        } else {
+            i = io.idx ? (uint64_t)io.idx[w] : w;
+            key = io.keys ? io.keys[w] : 0ull;
+        }
         uint64_t base, len;
         if (pb.offs) { base = pb.offs[i]; len = pb.offs[i + 1] - base; }
         else { base = i * (uint64_t)pb.fixed_len; len = pb.fixed_len; }
         const uint8_t* p = pb.pats + base;
-        P sp = 0, ep = 0;
         if (len == 0) {
             errbits |= ERRBIT_EMPTY_PATTERN;
         } else {
@@ -125,33 +168,47 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const uint64_t* __res
                 if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
                 return s;
             };
-            // CountArrayView::get_initial_pos_range_and_idx_of_pattern (count_array.rs:203-233)
-            uint64_t pi;
-            if (len < k) {
-                uint64_t start = 0;
-                for (uint64_t j = 0; j < len; j++) start += (uint64_t)(sym_at(j) + 1) * __ldg(ix.kmer_multiplier + j);
-                const uint64_t end = start + __ldg(ix.kmer_multiplier + (len - 1)) - 1;
-                sp = __ldg(ix.kmer_count_table + (start - 1));
-                ep = __ldg(ix.kmer_count_table + end);
-                pi = 0;
-            } else {
-                uint64_t start = 0;
-                for (uint32_t j = 0; j < k; j++) start += (uint64_t)(sym_at(len - k + j) + 1) * __ldg(ix.kmer_multiplier + j);
-                sp = __ldg(ix.kmer_count_table + (start - 1));
-                ep = __ldg(ix.kmer_count_table + start);
-                pi = len - k;
+            if (!RESUME) {
+                // CountArrayView::get_initial_pos_range_and_idx_of_pattern (count_array.rs:203-233)
+                if (len < k) {
+                    uint64_t start = 0;
+                    for (uint64_t j = 0; j < len; j++) start += (uint64_t)(sym_at(j) + 1) * __ldg(ix.kmer_multiplier + j);
+                    const uint64_t end = start + __ldg(ix.kmer_multiplier + (len - 1)) - 1;
+                    sp = __ldg(ix.kmer_count_table + (start - 1));
+                    ep = __ldg(ix.kmer_count_table + end);
+                    pi = 0;
+                } else {
+                    uint64_t start = 0;
+                    for (uint32_t j = 0; j < k; j++) start += (uint64_t)(sym_at(len - k + j) + 1) * __ldg(ix.kmer_multiplier + j);
+                    sp = __ldg(ix.kmer_count_table + (start - 1));
+                    ep = __ldg(ix.kmer_count_table + start);
+                    pi = len - k;
+                }
             }
             // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
-            while (sp < ep && pi > 0) {
+            uint32_t steps = io.max_steps;
+            while (sp < ep && pi > 0 && steps > 0) {
                 pi -= 1;
+                steps -= 1;
                 backward_step<P, NPL, VBITS>(ix, s_count, sym_at(pi), sp, ep);
             }
+            if (!(sp < ep)) pi = 0;  // empty interval: finished
         }
-        if (sp_work) sp_work[w] = sp;
-        cnt_work[w] = (P)(ep - sp);
-        if ((uint64_t)(ep - sp) > HEAVY_ROWS) atomicAdd(heavy_seen, 1ull);  // rare: sizes the heavy list
+        const P cnt = (P)(ep - sp);
+        if (io.sp_out) io.sp_out[w] = sp;
+        if (io.cnt_out) io.cnt_out[w] = cnt;
+        if (io.idx_out) io.idx_out[w] = (uint32_t)i;
+        if (io.items_out) {
+            Item<P> it;
+            it.key = key;
+            it.idx = (uint32_t)i;
+            it.pi = (uint32_t)pi;
+            it.cnt = cnt;
+            io.items_out[w] = it;
+        }
+        if (io.heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);  // rare: sizes the heavy list
     }
-    if (errbits) atomicOr(err, errbits);
+    if (errbits) atomicOr(io.err, errbits);
 }
 
 // FmIndex::write_locations_to_buffer (locate/mod.rs:14-37) for ONE SA row: LF-walk to the nearest

@@ -50,6 +50,7 @@ struct svfm_session {
     cudaStream_t stream = nullptr;
     svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
+    svfm::DeviceBuffer items0, items1, spk0, spk1;           // two-phase search: re-sort of the batch by sp
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
     svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
     unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
@@ -302,6 +303,7 @@ struct SortPlan {
     bool sorted = false;
     uint32_t bits = 0;     // bits per symbol in the packed key
     int begin_bit = 0, end_bit = 64;
+    uint32_t phase1_steps = 0;  // > 0: two-phase search, re-sorted by sp after this many backward steps
 };
 
 static std::atomic<uint64_t> g_sort_min{[] {
@@ -309,6 +311,10 @@ static std::atomic<uint64_t> g_sort_min{[] {
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 17);
 }()};
 static uint64_t sort_min_patterns() { return g_sort_min.load(); }
+static std::atomic<uint64_t> g_two_phase_min{[] {
+    const char* e = std::getenv("SVFM_TWO_PHASE_MIN");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : ~(uint64_t)0;  // off by default (round 1: not yet a win)
+}()};
 
 static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
     int b = 0;
@@ -332,6 +338,17 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n) {
     p.begin_bit = 64 - (int)(m * p.bits);
     p.end_bit = 64;
     p.sorted = true;
+    // Two-phase search for dense batches: phase 1 covers the suffix lengths at which the locality-sorted batch
+    // still has runs of >= ~4 patterns per distinct suffix (neighbouring lanes share rows); after that every
+    // interval is private and the batch is better off ordered by its SA position.
+    if (n >= g_two_phase_min.load()) {
+        uint32_t m1 = 0;
+        double distinct = 1.0;
+        while (distinct * s_eff * 4.0 <= (double)n) { distinct *= s_eff; m1++; }
+        const uint32_t k = ix->L.kmer_size;
+        if (m1 > k) p.phase1_steps = m1 - k;
+        else if (g_two_phase_min.load() == 0) p.phase1_steps = 1;  // forced (tests): exercise the path on tiny batches too
+    }
     return p;
 }
 
@@ -359,15 +376,85 @@ static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& 
     return SVFM_OK;
 }
 
+// One launch of the search kernel.  Single-phase: keys/idx (or NULL) in, sp/cnt out.
 template <class P, int NPL, int VBITS>
 static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
                       void* d_sp_work, void* d_cnt_work) {
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+    const int grid = resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
+    SearchIO<P> io{};
+    io.keys = keys;
+    io.idx = idx;
+    io.bits = bits;
+    io.max_steps = 0xffffffffu;
+    io.sp_out = (P*)d_sp_work;
+    io.cnt_out = (P*)d_cnt_work;
+    io.heavy_seen = s->d_counters;
+    io.err = s->d_err;
     PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, keys, idx, bits, (P*)d_sp_work,
-                                                                        (P*)d_cnt_work, s->d_counters, s->d_err);
+    search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
     SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+
+// Two-phase search of a locality-sorted batch: phase 1 (first `steps1` backward steps) -> radix sort of the
+// batch by its current sp -> phase 2 (RESUME) to the end.  Leaves sp/cnt in the new work order and the pattern
+// index of every work item in *idx_out.
+template <class P, int NPL, int VBITS>
+static int run_search_two_phase(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx,
+                                uint32_t bits, uint32_t steps1, void* d_sp_work, void* d_cnt_work,
+                                const uint32_t** idx_out) {
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    int rc;
+    if ((rc = s->items0.reserve(pb.n * sizeof(Item<P>))) || (rc = s->items1.reserve(pb.n * sizeof(Item<P>))) ||
+        (rc = s->spk0.reserve(pb.n * sizeof(P))) || (rc = s->spk1.reserve(pb.n * sizeof(P))))
+        return rc;
+    cub::DoubleBuffer<P> spk((P*)s->spk0.ptr, (P*)s->spk1.ptr);
+    cub::DoubleBuffer<Item<P>> items((Item<P>*)s->items0.ptr, (Item<P>*)s->items1.ptr);
+    // order inside an occ block does not matter: skip the low log2(BLOCK_LEN) bits
+    const int begin_bit = VecTraits<VBITS>::LOG2;
+    int end_bit = bits_for(s->ix->text_len + 1);
+    if (end_bit <= begin_bit) end_bit = begin_bit + 1;
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp, spk, items, (int64_t)pb.n, begin_bit, end_bit, s->stream));
+    if ((rc = s->cub_temp.reserve(temp))) return rc;
+    {
+        SearchIO<P> io{};
+        io.keys = keys;
+        io.idx = idx;
+        io.bits = bits;
+        io.max_steps = steps1;
+        io.sp_out = spk.Current();
+        io.items_out = items.Current();
+        io.err = s->d_err;
+        const int grid = resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
+        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+        search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+        SVFM_CUDA(cudaGetLastError());
+    }
+    {
+        PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (end_bit - begin_bit + 7) / 8);
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, spk, items, (int64_t)pb.n, begin_bit, end_bit, s->stream));
+    }
+    {
+        // the locality sort's index buffers are free once phase 1 has run (stream order): reuse one for idx_out
+        uint32_t* idx2 = (uint32_t*)s->vals0.ptr == idx ? (uint32_t*)s->vals1.ptr : (uint32_t*)s->vals0.ptr;
+        SearchIO<P> io{};
+        io.bits = bits;
+        io.max_steps = 0xffffffffu;
+        io.sp_in = spk.Current();
+        io.items_in = items.Current();
+        io.sp_out = (P*)d_sp_work;
+        io.cnt_out = (P*)d_cnt_work;
+        io.idx_out = idx2;
+        io.heavy_seen = s->d_counters;
+        io.err = s->d_err;
+        const int grid = resident_grid(search_kernel<P, NPL, VBITS, true>, pb.n, SEARCH_THREADS, s->ix->device);
+        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+        search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+        SVFM_CUDA(cudaGetLastError());
+        *idx_out = idx2;
+    }
     return SVFM_OK;
 }
 
@@ -532,6 +619,7 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
     } while (0)
 
 static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work); }
+static int dispatch_search_two_phase(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, uint32_t steps1, void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) { SVFM_DISPATCH(run_search_two_phase, s, pb, keys, idx, bits, steps1, d_sp_work, d_cnt_work, idx_out); }
 static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
 static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) { SVFM_DISPATCH(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out); }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) { SVFM_DISPATCH(run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key); }
@@ -557,7 +645,11 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     int rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
     if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
-    if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) return rc;
+    if (plan.phase1_steps) {
+        if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, nullptr, s->cnt.ptr, &idx))) return rc;
+    } else if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) {
+        return rc;
+    }
     return dispatch_sortback_counts(s, pb.n, idx, s->cnt.ptr, d_counts_out);
 }
 
@@ -582,7 +674,11 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
     }
-    if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) return rc;
+    if (plan.sorted && plan.phase1_steps) {
+        if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
+    } else if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) {
+        return rc;
+    }
     if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], offs_work + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -1029,6 +1125,7 @@ int svfm_set_tuning(int key, uint64_t value) {
     switch (key) {
         case SVFM_TUNE_SORT_MIN: g_sort_min.store(value); return SVFM_OK;
         case SVFM_TUNE_CHUNK: g_chunk_patterns.store(value); return SVFM_OK;
+        case SVFM_TUNE_TWO_PHASE_MIN: g_two_phase_min.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -53,7 +53,7 @@ int main() {
 
     // batched entry points
     auto counts = fm_index.count_batch({"TA", "UNDEF", "GGGG", "C"});
-    REQUIRE((counts == std::vector<uint32_t>{2, 2, 0, 7}));
+    REQUIRE((counts == std::vector<uint32_t>{2, 2, 0, 8}));
     auto lb = fm_index.locate_batch({"TA", "GGGG", "XXXXX"}, /*sorted=*/true);
     REQUIRE((lb.offsets == std::vector<uint64_t>{0, 2, 2, 4}));
     REQUIRE((lb.positions == std::vector<uint32_t>{5, 18, 25, 26}));

@@ -22,8 +22,11 @@ def fm(request):
     from sview_fmindex_b200 import _ffi
     value = {"sort_always": 0, "sort_never": 2**64 - 1, "sort_default": 1 << 17}[request.param]
     assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, value) == 0
+    # "sort_always" also forces the two-phase search (re-sort by SA position part-way) on every batch size
+    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 0 if request.param == "sort_always" else 2**64 - 1) == 0
     yield fm
     _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
+    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 2**64 - 1)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):

@@ -23,24 +23,21 @@ __global__ void gather(const uint8_t* buf, uint64_t sectors, uint64_t loads, uin
     if (acc == 0x1234567) atomicAdd(sink, 1ull);
 }
 int main() {
-    const uint64_t bytes = 687ull << 20, loads = 1ull << 28;
+    const uint64_t loads = 1ull << 28;
     uint8_t* buf; unsigned long long* sink;
-    cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes); cudaMalloc(&sink, 8);
+    const uint64_t maxb = 2688ull << 20;
+    cudaMalloc(&buf, maxb); cudaMemset(buf, 1, maxb); cudaMalloc(&sink, 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int gran : {0, 32, 64, 128}) {
-        if (gran) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); if (e) printf("set %d: %s\n", gran, cudaGetErrorString(e)); }
-        size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        for (int blocks : {148 * 8, 148 * 16}) {
-            float best8 = 1e9, best16 = 1e9;
+    for (uint64_t mb : {4ull, 16ull, 32ull, 64ull, 96ull, 128ull, 256ull, 687ull, 2688ull}) {
+        const uint64_t bytes = mb << 20;
+        for (int blocks : {148 * 8, 148 * 16, 148 * 32}) {
+            float best8 = 1e9;
             for (int it = 0; it < 4; it++) {
                 float ms;
                 cudaEventRecord(e0); gather<8, 8><<<blocks, 256>>>(buf, bytes / 32, loads, it, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
                 cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best8) best8 = ms;
-                cudaEventRecord(e0); gather<8, 16><<<blocks, 256>>>(buf, bytes / 32, loads, it, sink); cudaEventRecord(e1); cudaEventSynchronize(e1);
-                cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best16) best16 = ms;
             }
-            printf("gran set=%d got=%zu blocks=%d: 8B loads %.2f Gsect/s (%.2f ms)   16B loads %.2f Gsect/s\n", gran, got, blocks,
-                   loads / best8 / 1e6, best8, loads / best16 / 1e6);
+            printf("working set %4llu MB blocks=%d: %.1f Gsect/s (%.2f ms)\n", (unsigned long long)mb, blocks, loads / best8 / 1e6, best8);
         }
     }
     return 0;
