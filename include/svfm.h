@@ -168,8 +168,11 @@ void svfm_host_free(void* p);
  * batch into chunks of about this many patterns and pipeline upload / kernels / download over several
  * streams (0 = one chunk; default 16 Mi, or the SVFM_CHUNK environment variable).  SVFM_TUNE_TWO_PHASE_MIN:
  * locality-sorted batches with at least this many patterns are re-sorted by SA position part-way through the
- * backward search (default: never -- measured slower in round 1; or SVFM_TWO_PHASE_MIN).  Results never depend on any of them. */
-enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_TWO_PHASE_MIN = 2 };
+ * backward search (default: never -- measured slower in round 1; or SVFM_TWO_PHASE_MIN).  SVFM_TUNE_STREAM_MIN: fixed-length
+ * batches with at least this many patterns (that fit in a 64-bit key) use the streaming search (suffix-sorted batch,
+ * one launch per SVFM_TUNE_STREAM_STEPS backward steps; default 2 Mi / 1).  Results never depend on any of them. */
+enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_TWO_PHASE_MIN = 2, SVFM_TUNE_STREAM_MIN = 3,
+       SVFM_TUNE_STREAM_STEPS = 4 };
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */
 uint64_t svfm_launch_count(void);     /* kernels launched by this library since process start */

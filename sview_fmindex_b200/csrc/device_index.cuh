@@ -61,16 +61,36 @@ struct Block {
     using W = typename T::W;
     W w[NPL][T::WORDS];
 
+    // 64-bit words: the block is fetched with 16-byte loads (the blocks section is 32-byte aligned on the device,
+    // see svfm_load).  With an odd word count a block starts on an 8-byte boundary every other time: load the
+    // aligned window and shift by one word.  Fewer, wider loads matter because the L1 tag stage handles about one
+    // sector per cycle per SM (ncu, round 1: late backward steps were bound there, not in DRAM).
     __device__ __forceinline__ void load(const void* blocks, uint64_t q) {
-        const W* base = reinterpret_cast<const W*>(blocks) + q * (uint64_t)(NPL * T::WORDS);
+        constexpr int NW = NPL * T::WORDS;
+        if constexpr (sizeof(W) == 8) {
+            const uint64_t wi = q * (uint64_t)NW;
+            constexpr int CH = (NW + 2) / 2;  // chunks of two words covering NW (+1 when misaligned) words
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const W*>(blocks) + (wi & ~1ull));
+            unsigned long long raw[2 * CH];
 #pragma unroll
-        for (int v = 0; v < NPL; v++) {
-            if (T::WORDS == 1) {
-                w[v][0] = ld_gather<W>(base + v);
-            } else {
-                w[v][T::WORDS - 1] = ld_gather<W>(base + v * 2 + 0);  // low half  = symbols 64..127
-                w[v][0] = ld_gather<W>(base + v * 2 + 1);              // high half = symbols 0..63
+            for (int c = 0; c < CH; c++) {
+                if (2 * c < NW + (NW & 1)) {  // even NW: exactly NW/2 chunks; odd NW: (NW+1)/2 chunks
+                    const ulonglong2 v = __ldg(p + c);
+                    raw[2 * c] = v.x;
+                    raw[2 * c + 1] = v.y;
+                }
             }
+            const bool odd = (NW & 1) && (wi & 1ull);
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                const W word = (NW & 1) ? (odd ? raw[i + 1] : raw[i]) : raw[i];
+                if (T::WORDS == 1) w[i][0] = word;
+                else w[i / 2][(i & 1) ? 0 : T::WORDS - 1] = word;  // u128: low half first in memory
+            }
+        } else {
+            const W* base = reinterpret_cast<const W*>(blocks) + q * (uint64_t)NW;
+#pragma unroll
+            for (int v = 0; v < NPL; v++) w[v][0] = ld_gather<W>(base + v);
         }
     }
 

@@ -304,6 +304,7 @@ struct SortPlan {
     uint32_t bits = 0;     // bits per symbol in the packed key
     int begin_bit = 0, end_bit = 64;
     uint32_t phase1_steps = 0;  // > 0: two-phase search, re-sorted by sp after this many backward steps
+    uint32_t m1 = 0;            // > 0: streaming search (layout C keys sorted on their trailing m1 symbols)
 };
 
 static std::atomic<uint64_t> g_sort_min{[] {
@@ -322,7 +323,20 @@ static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
     return b;
 }
 
-static SortPlan plan_sort(const svfm_index* ix, uint64_t n) {
+static std::atomic<uint64_t> g_stream_min{[] {
+    const char* e = std::getenv("SVFM_STREAM_MIN");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(2u << 20);
+}()};
+static std::atomic<uint64_t> g_stream_steps{[] {
+    const char* e = std::getenv("SVFM_STREAM_STEPS");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)2;
+}()};
+static std::atomic<uint64_t> g_stream_run{[] {  // average patterns per distinct seed suffix
+    const char* e = std::getenv("SVFM_STREAM_RUN");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)16;
+}()};
+
+static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& pb) {
     SortPlan p;
     if (n < sort_min_patterns() || n > 0xffffffffull) return p;
     const uint32_t S = ix->L.symbol_count;
@@ -338,6 +352,20 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n) {
     p.begin_bit = 64 - (int)(m * p.bits);
     p.end_bit = 64;
     p.sorted = true;
+    // Streaming search: dense fixed-length batch whose patterns fit in the key.  m1 = longest suffix with, on
+    // average, >= 16 patterns per distinct suffix in the batch (clamped to [k, len]).
+    const uint32_t kk = ix->L.kmer_size;
+    if (!pb.offs && n >= g_stream_min.load() && pb.fixed_len >= kk && (uint64_t)pb.fixed_len * p.bits <= 64) {
+        uint32_t m1 = 0;
+        double distinct = 1.0;
+        while (distinct * s_eff * g_stream_run.load() <= (double)n && m1 < pb.fixed_len) { distinct *= s_eff; m1++; }
+        if (m1 < kk) m1 = kk;
+        if (g_stream_min.load() == 0 && m1 > kk && pb.fixed_len > kk + 1) m1 = kk + 1 + (m1 - kk) / 2;  // forced (tests): keep some steps for step_kernel
+        if (m1 > pb.fixed_len) m1 = pb.fixed_len;
+        p.m1 = m1;
+        p.begin_bit = 64 - (int)(m1 * p.bits);
+        return p;
+    }
     // Two-phase search for dense batches: phase 1 covers the suffix lengths at which the locality-sorted batch
     // still has runs of >= ~4 patterns per distinct suffix (neighbouring lanes share rows); after that every
     // interval is private and the batch is better off ordered by its SA position.
@@ -368,7 +396,7 @@ static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& 
     const svfm_index* ix = s->ix;
     const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
     pack_keys_kernel<<<resident_grid(pack_keys_kernel, pb.n, SEARCH_THREADS, ix->device), SEARCH_THREADS, 0, s->stream>>>(
-        table, ix->L.symbol_count, pb, plan.bits, keys.Current(), vals.Current(), s->d_err);
+        table, ix->L.symbol_count, pb, plan.bits, plan.m1, keys.Current(), vals.Current(), s->d_err);
     SVFM_CUDA(cudaGetLastError());
     SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, keys, vals, (int64_t)pb.n, plan.begin_bit, plan.end_bit, s->stream));
     *keys_out = keys.Current();
@@ -454,6 +482,33 @@ static int run_search_two_phase(svfm_session* s, const PatternBatch& pb, const u
         search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
         SVFM_CUDA(cudaGetLastError());
         *idx_out = idx2;
+    }
+    return SVFM_OK;
+}
+
+// Streaming search of a dense fixed-length batch (keys in layout C, sorted on their trailing m1 symbols):
+// seed_kernel (once per run of equal suffixes) + step_kernel launches for the remaining symbols.
+template <class P, int NPL, int VBITS>
+static int run_search_stream(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, uint32_t bits, uint32_t m1,
+                             void* d_sp_work, void* d_cnt_work) {
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    const uint32_t len = pb.fixed_len;
+    const uint32_t per_launch = (uint32_t)(g_stream_steps.load() ? g_stream_steps.load() : 1);
+    const uint32_t launches = (len - m1 + per_launch - 1) / per_launch;
+    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1 + launches);
+    {
+        const int grid = resident_grid(seed_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+        seed_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, keys, pb.n, bits, m1, (P*)d_sp_work, (P*)d_cnt_work,
+                                                                          launches == 0 ? s->d_counters : nullptr);
+        SVFM_CUDA(cudaGetLastError());
+    }
+    const int grid = resident_grid(step_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+    for (uint32_t j = m1; j < len; j += per_launch) {
+        const uint32_t steps = len - j < per_launch ? len - j : per_launch;
+        const bool last = j + steps >= len;
+        step_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, keys, pb.n, bits, m1, j, steps, (P*)d_sp_work,
+                                                                          (P*)d_cnt_work, last ? s->d_counters : nullptr);
+        SVFM_CUDA(cudaGetLastError());
     }
     return SVFM_OK;
 }
@@ -620,6 +675,7 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
 
 static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work); }
 static int dispatch_search_two_phase(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, uint32_t steps1, void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) { SVFM_DISPATCH(run_search_two_phase, s, pb, keys, idx, bits, steps1, d_sp_work, d_cnt_work, idx_out); }
+static int dispatch_search_stream(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, uint32_t bits, uint32_t m1, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search_stream, s, pb, keys, bits, m1, d_sp_work, d_cnt_work); }
 static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
 static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) { SVFM_DISPATCH(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out); }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) { SVFM_DISPATCH(run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key); }
@@ -637,7 +693,7 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
     SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
     if (pb.n == 0) return SVFM_OK;
-    const SortPlan plan = plan_sort(s->ix, pb.n);
+    const SortPlan plan = plan_sort(s->ix, pb.n, pb);
     if (!plan.sorted) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
     const uint64_t P = s->ix->type.pos_bits / 8;
     const uint64_t* keys = nullptr;
@@ -645,7 +701,10 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     int rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
     if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
-    if (plan.phase1_steps) {
+    if (plan.m1) {
+        if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
+        if ((rc = dispatch_search_stream(s, pb, keys, plan.bits, plan.m1, s->sp.ptr, s->cnt.ptr))) return rc;
+    } else if (plan.phase1_steps) {
         if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, nullptr, s->cnt.ptr, &idx))) return rc;
     } else if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) {
         return rc;
@@ -665,7 +724,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
     if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
-    const SortPlan plan = plan_sort(s->ix, pb.n);
+    const SortPlan plan = plan_sort(s->ix, pb.n, pb);
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
     uint64_t* offs_work = d_out_offs;  // small batch: work order == caller order
@@ -674,7 +733,9 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
     }
-    if (plan.sorted && plan.phase1_steps) {
+    if (plan.sorted && plan.m1) {
+        if ((rc = dispatch_search_stream(s, pb, keys, plan.bits, plan.m1, s->sp.ptr, s->cnt.ptr))) return rc;
+    } else if (plan.sorted && plan.phase1_steps) {
         if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
     } else if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) {
         return rc;
@@ -1126,6 +1187,8 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_SORT_MIN: g_sort_min.store(value); return SVFM_OK;
         case SVFM_TUNE_CHUNK: g_chunk_patterns.store(value); return SVFM_OK;
         case SVFM_TUNE_TWO_PHASE_MIN: g_two_phase_min.store(value); return SVFM_OK;
+        case SVFM_TUNE_STREAM_MIN: g_stream_min.store(value); return SVFM_OK;
+        case SVFM_TUNE_STREAM_STEPS: g_stream_steps.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

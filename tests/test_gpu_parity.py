@@ -24,9 +24,12 @@ def fm(request):
     assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, value) == 0
     # "sort_always" also forces the two-phase search (re-sort by SA position part-way) on every batch size
     assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 0 if request.param == "sort_always" else 2**64 - 1) == 0
+    # ... and the streaming search (suffix-sorted batch, seed + per-step kernels) on every fixed-length batch
+    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_STREAM_MIN, 0 if request.param == "sort_always" else 2 << 20) == 0
     yield fm
     _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
     _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 2**64 - 1)
+    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_STREAM_MIN, 2 << 20)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
