@@ -149,11 +149,12 @@ int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint6
  * launches[] = kernels launched in the phase.  Reading synchronises the session's stream. */
 enum {
     SVFM_PHASE_PRESORT = 0, /* pattern encoding/packing + locality sort of the batch */
-    SVFM_PHASE_SEARCH = 1,  /* backward-search kernel (count) */
+    SVFM_PHASE_SEARCH = 1,  /* backward-search kernels (search_kernel / sweep_step_kernel) */
     SVFM_PHASE_SCAN = 2,    /* exclusive prefix sum of the counts -> CSR offsets */
     SVFM_PHASE_LOCATE = 3,  /* LF-walk + sampled-SA lookup kernel */
     SVFM_PHASE_SEGSORT = 4, /* optional per-pattern sort of the positions (SVFM_SORTED) */
-    SVFM_PHASE_OTHER = 5,   /* permutation / scatter helpers */
+    SVFM_PHASE_OTHER = 5,   /* back to the caller's order: radix sort by pattern index, CSR offsets */
+    SVFM_PHASE_PARTITION = 6, /* sweep search: radix partition of the batch between rounds of backward steps */
     SVFM_PHASE_MAX = 8
 };
 int svfm_session_set_timing(svfm_session* s, int enabled);
@@ -162,17 +163,19 @@ int svfm_session_get_timing(svfm_session* s, double ms[SVFM_PHASE_MAX], uint64_t
 /* ---- misc -------------------------------------------------------------------------------------- */
 void* svfm_host_alloc(size_t bytes);  /* pinned host memory (cudaHostAlloc) or NULL */
 void svfm_host_free(void* p);
-/* Process-wide tuning knobs.  SVFM_TUNE_SORT_MIN: batches with at least this many patterns are
- * locality-sorted by their trailing symbols before the search (0 = always, UINT64_MAX = never; default
- * 131072, or the SVFM_SORT_MIN environment variable).  SVFM_TUNE_CHUNK: the host-buffer entry points cut a
- * batch into chunks of about this many patterns and pipeline upload / kernels / download over several
- * streams (0 = one chunk; default 16 Mi, or the SVFM_CHUNK environment variable).  SVFM_TUNE_TWO_PHASE_MIN:
- * locality-sorted batches with at least this many patterns are re-sorted by SA position part-way through the
- * backward search (default: never -- measured slower in round 1; or SVFM_TWO_PHASE_MIN).  SVFM_TUNE_STREAM_MIN: fixed-length
- * batches with at least this many patterns (that fit in a 64-bit key) use the streaming search (suffix-sorted batch,
- * one launch per SVFM_TUNE_STREAM_STEPS backward steps; default 2 Mi / 1).  Results never depend on any of them. */
-enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_TWO_PHASE_MIN = 2, SVFM_TUNE_STREAM_MIN = 3,
-       SVFM_TUNE_STREAM_STEPS = 4 };
+/* Process-wide tuning knobs; results never depend on any of them.
+ * SVFM_TUNE_SORT_MIN : batches with at least this many patterns (that do not qualify for the sweep search) are
+ *                      locality-sorted by their trailing symbols before the search kernel (0 = always,
+ *                      UINT64_MAX = never; default 131072; env SVFM_SORT_MIN).
+ * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
+ *                      pipeline upload / kernels / download (0 = one chunk; default 16 Mi; env SVFM_CHUNK).
+ * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
+ *                      kept sorted by SA position and moves through the index as streams (default 1 Mi; env
+ *                      SVFM_SWEEP_MIN).
+ * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries, derived
+ *                      from the blob at load (0 = none; default 24 = 128 MiB for u32 positions; env SVFM_EXT_BITS).
+ * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS). */
+enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4 };
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */
 uint64_t svfm_launch_count(void);     /* kernels launched by this library since process start */

@@ -30,9 +30,9 @@ SVFM_ERR_CUDA = 30
 
 SVFM_TUNE_SORT_MIN = 0
 SVFM_TUNE_CHUNK = 1
-SVFM_TUNE_TWO_PHASE_MIN = 2
-SVFM_TUNE_STREAM_MIN = 3
-SVFM_TUNE_STREAM_STEPS = 4
+SVFM_TUNE_SWEEP_MIN = 2
+SVFM_TUNE_EXT_BITS = 3
+SVFM_TUNE_WORKERS = 4
 SVFM_REVERSED = 1
 SVFM_SORTED = 2
 

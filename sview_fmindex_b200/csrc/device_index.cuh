@@ -26,7 +26,19 @@ struct DevIndex {
     uint32_t sampling_ratio;          // r
     uint32_t ratio_mask;              // r-1 if r is a power of two, else 0xffffffff
     uint32_t ratio_shift;             // log2(r) if power of two
-    uint64_t kmer_top_multiplier;     // (S+1)^(k-1) = kmer_multiplier[0]
+    // extended k-mer table derived from the blob at load (search_kernels.cuh): P[2 * s_eff^ext_m] (sp, count)
+    const P* ext;                     // NULL = not built
+    uint32_t ext_m;                   // symbols resolved by one lookup
+    uint32_t s_eff;                   // symbols that occur in the text
+    uint8_t sym_rank[64];             // symbol index -> rank among the occurring symbols, 0xff = never occurs
+    uint8_t present[64];              // rank -> symbol index
+};
+
+// the symbol maps alone (kernels that do not touch the index arrays)
+struct DevSyms {
+    uint32_t symbol_count;
+    uint32_t s_eff;
+    uint8_t sym_rank[64];
 };
 
 // ---- loads --------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -41,6 +42,11 @@ struct svfm_index {
     uint64_t text_len = 0;
     uint64_t sentinel_index = 0;
     uint32_t symbols_present = 0;  // symbols with at least one occurrence in the text (from count_array)
+    uint8_t sym_rank[64];          // symbol index -> rank among the occurring symbols (0xff: never occurs)
+    uint8_t present[64];           // rank -> symbol index
+    uint32_t ext_m = 0;            // extended k-mer table: symbols resolved per lookup (0 = no table)
+    uint64_t ext_entries = 0;
+    void* d_ext = nullptr;         // P[2 * ext_entries]
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
 };
@@ -50,7 +56,7 @@ struct svfm_session {
     cudaStream_t stream = nullptr;
     svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
-    svfm::DeviceBuffer items0, items1, spk0, spk1;           // two-phase search: re-sort of the batch by sp
+    svfm::DeviceBuffer pay0, pay1, rest0, rest1, val0, val1; // sweep search: items moving through the radix partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
     svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
     unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
@@ -91,7 +97,11 @@ static DevIndex<P> make_dev_index(const svfm_index* ix) {
         d.ratio_mask = 0xffffffffu;
         d.ratio_shift = 0;
     }
-    d.kmer_top_multiplier = 0;
+    d.ext = reinterpret_cast<const P*>(ix->d_ext);
+    d.ext_m = ix->ext_m;
+    d.s_eff = ix->symbols_present;
+    std::memcpy(d.sym_rank, ix->sym_rank, 64);
+    std::memcpy(d.present, ix->present, 64);
     return d;
 }
 
@@ -107,10 +117,16 @@ static int finish_load(svfm_index* ix) {
         SVFM_CUDA(cudaMemcpy(ca, ix->d_blob + L.off_count_array, (uint64_t)L.count_array_len * P, cudaMemcpyDeviceToHost));
         uint64_t prev = 0;
         ix->symbols_present = 0;
-        for (uint32_t i = 1; i < L.count_array_len; i++) {
+        std::memset(ix->sym_rank, 0xff, 64);
+        std::memset(ix->present, 0, 64);
+        for (uint32_t i = 1; i < L.count_array_len && i <= 64; i++) {
             uint64_t c = 0;
             std::memcpy(&c, ca + i * P, P);
-            if (c > prev) ix->symbols_present++;
+            if (c > prev) {  // symbol i-1 occurs count_array[i] - count_array[i-1] times
+                ix->sym_rank[i - 1] = (uint8_t)ix->symbols_present;
+                ix->present[ix->symbols_present] = (uint8_t)(i - 1);
+                ix->symbols_present++;
+            }
             prev = c;
         }
     }
@@ -125,6 +141,8 @@ static int finish_load(svfm_index* ix) {
     if (ix->text_len / r + (ix->text_len % r ? 1 : 0) != L.suffix_array_len) return SVFM_ERR_INVALID_FORMAT;
     return SVFM_OK;
 }
+
+static int build_ext_table(svfm_index* ix);
 
 static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int device, bool src_on_device,
                        svfm_index** out, uint64_t err_detail[2]) {
@@ -170,7 +188,9 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
         return SVFM_ERR_CUDA;
     }
     rc = finish_load(ix);
+    if (rc == SVFM_OK) rc = build_ext_table(ix);
     if (rc) {
+        if (ix->d_ext) cudaFree(ix->d_ext);
         cudaFree(ix->d_alloc);
         delete ix;
         return rc;
@@ -295,16 +315,21 @@ static int grid_for(uint64_t work_items, int threads, int device) {
     return (int)blocks;
 }
 
-// Locality sort of the batch (SVFM_PHASE_PRESORT): patterns ordered by their trailing symbols so that
-// neighbouring threads of the search kernel walk neighbouring checkpoint rows / blocks.  Everything that has
-// to change order afterwards moves through radix sorts (streaming passes), never through random scatters:
-// on B200 one random 32 B sector access costs as much HBM time as streaming ~500 bytes.
+// Batch plans.  Everything that has to change order moves through radix sorts (streaming passes), never through
+// random scatters: on B200 one random 32 B sector access costs as much HBM time as streaming ~120 bytes.
+//   sweep  : dense fixed-length batch -> items sorted by SA interval, rounds of backward steps + radix partition
+//            (search_kernels.cuh, "sweep search")
+//   sorted : locality sort by trailing symbols, one search kernel (variable-length or long patterns)
+//   neither: search kernel in the caller's order (small batches)
 struct SortPlan {
     bool sorted = false;
     uint32_t bits = 0;     // bits per symbol in the packed key
     int begin_bit = 0, end_bit = 64;
-    uint32_t phase1_steps = 0;  // > 0: two-phase search, re-sorted by sp after this many backward steps
-    uint32_t m1 = 0;            // > 0: streaming search (layout C keys sorted on their trailing m1 symbols)
+    bool sweep = false;
+    uint32_t m = 0;            // sweep: trailing symbols resolved by the extended table
+    int prefix_bits = 0;       // sweep: significant bits of the table index
+    uint32_t steps_per_round = 1;
+    bool rest64 = false;       // sweep: the other symbols need a 64-bit word
 };
 
 static std::atomic<uint64_t> g_sort_min{[] {
@@ -312,9 +337,17 @@ static std::atomic<uint64_t> g_sort_min{[] {
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 17);
 }()};
 static uint64_t sort_min_patterns() { return g_sort_min.load(); }
-static std::atomic<uint64_t> g_two_phase_min{[] {
-    const char* e = std::getenv("SVFM_TWO_PHASE_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : ~(uint64_t)0;  // off by default (round 1: not yet a win)
+static std::atomic<uint64_t> g_sweep_min{[] {
+    const char* e = std::getenv("SVFM_SWEEP_MIN");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 20);
+}()};
+static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
+    const char* e = std::getenv("SVFM_EXT_BITS");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)24;
+}()};
+static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once more after the last round
+    const char* e = std::getenv("SVFM_SWEEP_FINAL_SORT");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
 
 static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
@@ -323,25 +356,23 @@ static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
     return b;
 }
 
-static std::atomic<uint64_t> g_stream_min{[] {
-    const char* e = std::getenv("SVFM_STREAM_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(2u << 20);
-}()};
-static std::atomic<uint64_t> g_stream_steps{[] {
-    const char* e = std::getenv("SVFM_STREAM_STEPS");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)2;
-}()};
-static std::atomic<uint64_t> g_stream_run{[] {  // average patterns per distinct seed suffix
-    const char* e = std::getenv("SVFM_STREAM_RUN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)16;
-}()};
-
 static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& pb) {
     SortPlan p;
-    if (n < sort_min_patterns() || n > 0xffffffffull) return p;
     const uint32_t S = ix->L.symbol_count;
     p.bits = (uint32_t)bits_for(S);
     if (p.bits == 0) p.bits = 1;
+    if (n > 0xffffffffull) return p;
+    if (!pb.offs && ix->ext_m && n >= g_sweep_min.load() && pb.fixed_len >= ix->ext_m &&
+        (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits <= 64) {
+        p.sweep = true;
+        p.m = ix->ext_m;
+        p.prefix_bits = bits_for(ix->ext_entries) < 1 ? 1 : bits_for(ix->ext_entries);
+        p.rest64 = (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits > 32;
+        const uint32_t t = 8u / p.bits;  // one radix pass (8-bit digit) per partition
+        p.steps_per_round = t < 1 ? 1 : (t > 3 ? 3 : t);
+        return p;
+    }
+    if (n < sort_min_patterns()) return p;
     // Sort on as many trailing symbols as it takes to tell the occ blocks apart: log_{S_eff}(blocks) + 1
     // symbols, S_eff = symbols that actually occur in the text (count_array).
     const double s_eff = ix->symbols_present > 1 ? (double)ix->symbols_present : 2.0;
@@ -352,31 +383,6 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
     p.begin_bit = 64 - (int)(m * p.bits);
     p.end_bit = 64;
     p.sorted = true;
-    // Streaming search: dense fixed-length batch whose patterns fit in the key.  m1 = longest suffix with, on
-    // average, >= 16 patterns per distinct suffix in the batch (clamped to [k, len]).
-    const uint32_t kk = ix->L.kmer_size;
-    if (!pb.offs && n >= g_stream_min.load() && pb.fixed_len >= kk && (uint64_t)pb.fixed_len * p.bits <= 64) {
-        uint32_t m1 = 0;
-        double distinct = 1.0;
-        while (distinct * s_eff * g_stream_run.load() <= (double)n && m1 < pb.fixed_len) { distinct *= s_eff; m1++; }
-        if (m1 < kk) m1 = kk;
-        if (g_stream_min.load() == 0 && m1 > kk && pb.fixed_len > kk + 1) m1 = kk + 1 + (m1 - kk) / 2;  // forced (tests): keep some steps for step_kernel
-        if (m1 > pb.fixed_len) m1 = pb.fixed_len;
-        p.m1 = m1;
-        p.begin_bit = 64 - (int)(m1 * p.bits);
-        return p;
-    }
-    // Two-phase search for dense batches: phase 1 covers the suffix lengths at which the locality-sorted batch
-    // still has runs of >= ~4 patterns per distinct suffix (neighbouring lanes share rows); after that every
-    // interval is private and the batch is better off ordered by its SA position.
-    if (n >= g_two_phase_min.load()) {
-        uint32_t m1 = 0;
-        double distinct = 1.0;
-        while (distinct * s_eff * 4.0 <= (double)n) { distinct *= s_eff; m1++; }
-        const uint32_t k = ix->L.kmer_size;
-        if (m1 > k) p.phase1_steps = m1 - k;
-        else if (g_two_phase_min.load() == 0) p.phase1_steps = 1;  // forced (tests): exercise the path on tiny batches too
-    }
     return p;
 }
 
@@ -396,7 +402,7 @@ static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& 
     const svfm_index* ix = s->ix;
     const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
     pack_keys_kernel<<<resident_grid(pack_keys_kernel, pb.n, SEARCH_THREADS, ix->device), SEARCH_THREADS, 0, s->stream>>>(
-        table, ix->L.symbol_count, pb, plan.bits, plan.m1, keys.Current(), vals.Current(), s->d_err);
+        table, ix->L.symbol_count, pb, plan.bits, keys.Current(), vals.Current(), s->d_err);
     SVFM_CUDA(cudaGetLastError());
     SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, keys, vals, (int64_t)pb.n, plan.begin_bit, plan.end_bit, s->stream));
     *keys_out = keys.Current();
@@ -404,113 +410,160 @@ static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& 
     return SVFM_OK;
 }
 
-// One launch of the search kernel.  Single-phase: keys/idx (or NULL) in, sp/cnt out.
+// One launch of the search kernel: keys/idx (or NULL) in, sp/cnt out.
 template <class P, int NPL, int VBITS>
 static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
                       void* d_sp_work, void* d_cnt_work) {
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const int grid = resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
+    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
     SearchIO<P> io{};
     io.keys = keys;
     io.idx = idx;
     io.bits = bits;
-    io.max_steps = 0xffffffffu;
     io.sp_out = (P*)d_sp_work;
     io.cnt_out = (P*)d_cnt_work;
     io.heavy_seen = s->d_counters;
     io.err = s->d_err;
     PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-    search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
     SVFM_CUDA(cudaGetLastError());
     return SVFM_OK;
 }
 
-// Two-phase search of a locality-sorted batch: phase 1 (first `steps1` backward steps) -> radix sort of the
-// batch by its current sp -> phase 2 (RESUME) to the end.  Leaves sp/cnt in the new work order and the pattern
-// index of every work item in *idx_out.
+// Extended k-mer table, built once per index right after the upload (search_kernels.cuh).
 template <class P, int NPL, int VBITS>
-static int run_search_two_phase(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx,
-                                uint32_t bits, uint32_t steps1, void* d_sp_work, void* d_cnt_work,
-                                const uint32_t** idx_out) {
-    const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    int rc;
-    if ((rc = s->items0.reserve(pb.n * sizeof(Item<P>))) || (rc = s->items1.reserve(pb.n * sizeof(Item<P>))) ||
-        (rc = s->spk0.reserve(pb.n * sizeof(P))) || (rc = s->spk1.reserve(pb.n * sizeof(P))))
-        return rc;
-    cub::DoubleBuffer<P> spk((P*)s->spk0.ptr, (P*)s->spk1.ptr);
-    cub::DoubleBuffer<Item<P>> items((Item<P>*)s->items0.ptr, (Item<P>*)s->items1.ptr);
-    // order inside an occ block does not matter: skip the low log2(BLOCK_LEN) bits
-    const int begin_bit = VecTraits<VBITS>::LOG2;
-    int end_bit = bits_for(s->ix->text_len + 1);
-    if (end_bit <= begin_bit) end_bit = begin_bit + 1;
-    size_t temp = 0;
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp, spk, items, (int64_t)pb.n, begin_bit, end_bit, s->stream));
-    if ((rc = s->cub_temp.reserve(temp))) return rc;
-    {
-        SearchIO<P> io{};
-        io.keys = keys;
-        io.idx = idx;
-        io.bits = bits;
-        io.max_steps = steps1;
-        io.sp_out = spk.Current();
-        io.items_out = items.Current();
-        io.err = s->d_err;
-        const int grid = resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
-        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-        search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
-        SVFM_CUDA(cudaGetLastError());
+static int run_build_ext(svfm_index* ix, int unused) {
+    (void)unused;
+    const uint64_t s_eff = ix->symbols_present;
+    uint64_t budget = 1ull << (g_ext_bits.load() > 32 ? 32 : g_ext_bits.load());
+    if (g_ext_bits.load() == 0 || s_eff < 2 || s_eff > 64) return SVFM_OK;
+    const uint64_t by_text = ix->text_len / 2 > s_eff ? ix->text_len / 2 : s_eff;
+    if (budget > by_text) budget = by_text;
+    uint32_t m = 1;
+    uint64_t entries = s_eff;
+    while (entries * s_eff <= budget && m < 31) { entries *= s_eff; m++; }
+    if (entries > 0xfffffff0ull) return SVFM_OK;
+    DevIndex<P> dix = make_dev_index<P>(ix);
+    P *a = nullptr, *b = nullptr;
+    SVFM_CUDA(cudaMalloc(&a, entries * 2 * sizeof(P)));
+    if (m > 1) {
+        cudaError_t e = cudaMalloc(&b, entries / s_eff * 2 * sizeof(P));
+        if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
     }
-    {
-        PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (end_bit - begin_bit + 7) / 8);
-        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, temp, spk, items, (int64_t)pb.n, begin_bit, end_bit, s->stream));
+    // levels alternate between the two buffers so that level m lands in `a`
+    P* cur = (m % 2 == 1) ? a : b;
+    P* other = (m % 2 == 1) ? b : a;
+    ext_level1_kernel<P><<<1, 64>>>(dix, cur);
+    g_launches++;
+    uint64_t n_in = s_eff;
+    for (uint32_t j = 1; j < m; j++) {
+        const int grid = resident_grid(ext_expand_kernel<P, NPL, VBITS>, n_in * s_eff, SEARCH_THREADS, ix->device);
+        ext_expand_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS>>>(dix, cur, n_in, other);
+        g_launches++;
+        std::swap(cur, other);
+        n_in *= s_eff;
     }
-    {
-        // the locality sort's index buffers are free once phase 1 has run (stream order): reuse one for idx_out
-        uint32_t* idx2 = (uint32_t*)s->vals0.ptr == idx ? (uint32_t*)s->vals1.ptr : (uint32_t*)s->vals0.ptr;
-        SearchIO<P> io{};
-        io.bits = bits;
-        io.max_steps = 0xffffffffu;
-        io.sp_in = spk.Current();
-        io.items_in = items.Current();
-        io.sp_out = (P*)d_sp_work;
-        io.cnt_out = (P*)d_cnt_work;
-        io.idx_out = idx2;
-        io.heavy_seen = s->d_counters;
-        io.err = s->d_err;
-        const int grid = resident_grid(search_kernel<P, NPL, VBITS, true>, pb.n, SEARCH_THREADS, s->ix->device);
-        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-        search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
-        SVFM_CUDA(cudaGetLastError());
-        *idx_out = idx2;
-    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (b) cudaFree(b);
+    if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
+    ix->d_ext = a;
+    ix->ext_m = m;
+    ix->ext_entries = entries;
     return SVFM_OK;
 }
 
-// Streaming search of a dense fixed-length batch (keys in layout C, sorted on their trailing m1 symbols):
-// seed_kernel (once per run of equal suffixes) + step_kernel launches for the remaining symbols.
-template <class P, int NPL, int VBITS>
-static int run_search_stream(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, uint32_t bits, uint32_t m1,
-                             void* d_sp_work, void* d_cnt_work) {
-    const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const uint32_t len = pb.fixed_len;
-    const uint32_t per_launch = (uint32_t)(g_stream_steps.load() ? g_stream_steps.load() : 1);
-    const uint32_t launches = (len - m1 + per_launch - 1) / per_launch;
-    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1 + launches);
+// Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps,
+// stable radix partition by the consumed symbols].  Leaves sp/cnt/idx of every item in work order.
+template <class P, int NPL, int VBITS, class R>
+static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
+                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {
+    const svfm_index* ix = s->ix;
+    const DevIndex<P> dix = make_dev_index<P>(ix);
+    const uint64_t n = pb.n;
+    const uint32_t len = pb.fixed_len, m = plan.m, bits = plan.bits, T = plan.steps_per_round;
+    const uint32_t remaining = len - m;
+    const uint32_t rounds = remaining ? (remaining + T - 1) / T : 1;
+    using Pay = SweepPay<R>;
+    using Val = SweepVal<P>;
+    int rc;
+    if ((rc = s->keys0.reserve(n * 4)) || (rc = s->keys1.reserve(n * 4)) || (rc = s->pay0.reserve(n * sizeof(Pay))) ||
+        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->vals0.reserve(n * 4)))
+        return rc;
+    const bool partitions = rounds > 1 || final_sort;
+    if (partitions && ((rc = s->rest0.reserve(n * sizeof(R))) || (rc = s->rest1.reserve(n * sizeof(R))) ||
+                       (rc = s->val0.reserve(n * sizeof(Val))) || (rc = s->val1.reserve(n * sizeof(Val)))))
+        return rc;
+    cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
+    cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
+    cub::DoubleBuffer<R> rest((R*)s->rest0.ptr, (R*)s->rest1.ptr);
+    cub::DoubleBuffer<Val> val((Val*)s->val0.ptr, (Val*)s->val1.ptr);
+    size_t t1 = 0, t2 = 0;
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
+    if (partitions) SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, rest, val, (int64_t)n, 0, (int)(bits * T), s->stream));
+    if ((rc = s->cub_temp.reserve(t1 > t2 ? t1 : t2))) return rc;
     {
-        const int grid = resident_grid(seed_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
-        seed_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, keys, pb.n, bits, m1, (P*)d_sp_work, (P*)d_cnt_work,
-                                                                          launches == 0 ? s->d_counters : nullptr);
+        PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits + 7) / 8);
+        const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
+        DevSyms syms;
+        syms.symbol_count = ix->L.symbol_count;
+        syms.s_eff = ix->symbols_present;
+        std::memcpy(syms.sym_rank, ix->sym_rank, 64);
+        const size_t smem = ((size_t)SEARCH_THREADS * len + 15) & ~(size_t)15;
+        int grid = grid_for(n, SEARCH_THREADS, ix->device);
+        pack_sweep_kernel<R><<<grid, SEARCH_THREADS, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(), s->d_err);
         SVFM_CUDA(cudaGetLastError());
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
     }
-    const int grid = resident_grid(step_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
-    for (uint32_t j = m1; j < len; j += per_launch) {
-        const uint32_t steps = len - j < per_launch ? len - j : per_launch;
-        const bool last = j + steps >= len;
-        step_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, keys, pb.n, bits, m1, j, steps, (P*)d_sp_work,
-                                                                          (P*)d_cnt_work, last ? s->d_counters : nullptr);
-        SVFM_CUDA(cudaGetLastError());
+    uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t first = r * T;
+        const uint32_t steps = remaining - first < T ? remaining - first : T;
+        const bool last = r + 1 == rounds;
+        const bool sort_after = !last || final_sort;
+        SweepIO<P, R> io{};
+        if (r == 0) { io.prefix = prefix.Current(); io.pay = pay.Current(); }
+        else { io.rest_in = rest.Current(); io.val_in = val.Current(); }
+        if (sort_after) {
+            io.rest_out = r == 0 ? rest.Current() : nullptr;  // later rounds: rest is already in place
+            io.val_out = val.Current();
+        } else {
+            io.sp_out = (P*)d_sp_work;
+            io.cnt_out = (P*)d_cnt_work;
+            io.idx_out = idx_work;
+        }
+        if (last) io.heavy_seen = s->d_counters;
+        {
+            PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+            if (r == 0) {
+                const int grid = resident_grid(sweep_step_kernel<P, NPL, VBITS, R, true>, n, SEARCH_THREADS, ix->device);
+                sweep_step_kernel<P, NPL, VBITS, R, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, n, bits, bits * first, steps, io);
+            } else {
+                const int grid = resident_grid(sweep_step_kernel<P, NPL, VBITS, R, false>, n, SEARCH_THREADS, ix->device);
+                sweep_step_kernel<P, NPL, VBITS, R, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, n, bits, bits * first, steps, io);
+            }
+            SVFM_CUDA(cudaGetLastError());
+        }
+        if (sort_after && steps) {
+            PhaseTimer pt(s, SVFM_PHASE_PARTITION, 3);
+            SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t2, rest, val, (int64_t)n, (int)(bits * first),
+                                                      (int)(bits * (first + steps)), s->stream));
+        }
+        if (last && sort_after) {
+            PhaseTimer pt(s, SVFM_PHASE_PARTITION, 1);
+            sweep_unzip_kernel<P><<<grid_for(n, SEARCH_THREADS, ix->device), SEARCH_THREADS, 0, s->stream>>>(
+                val.Current(), n, (P*)d_sp_work, (P*)d_cnt_work, idx_work);
+            SVFM_CUDA(cudaGetLastError());
+        }
     }
+    *idx_out = idx_work;
     return SVFM_OK;
+}
+
+template <class P, int NPL, int VBITS>
+static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
+                            void* d_cnt_work, const uint32_t** idx_out) {
+    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
+    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
 }
 
 template <class P>
@@ -674,8 +727,11 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
     } while (0)
 
 static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work); }
-static int dispatch_search_two_phase(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, uint32_t steps1, void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) { SVFM_DISPATCH(run_search_two_phase, s, pb, keys, idx, bits, steps1, d_sp_work, d_cnt_work, idx_out); }
-static int dispatch_search_stream(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, uint32_t bits, uint32_t m1, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search_stream, s, pb, keys, bits, m1, d_sp_work, d_cnt_work); }
+static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) { SVFM_DISPATCH(run_search_sweep, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out); }
+static int build_ext_table(svfm_index* ix) {
+    struct { svfm_index* ix; } shim{ix}, *s = &shim;
+    SVFM_DISPATCH(run_build_ext, ix, 0);
+}
 static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
 static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) { SVFM_DISPATCH(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out); }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) { SVFM_DISPATCH(run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key); }
@@ -694,20 +750,18 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
     if (pb.n == 0) return SVFM_OK;
     const SortPlan plan = plan_sort(s->ix, pb.n, pb);
-    if (!plan.sorted) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
+    if (!plan.sorted && !plan.sweep) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
     const uint64_t P = s->ix->type.pos_bits / 8;
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
     int rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
-    if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
-    if (plan.m1) {
+    if (plan.sweep) {
         if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
-        if ((rc = dispatch_search_stream(s, pb, keys, plan.bits, plan.m1, s->sp.ptr, s->cnt.ptr))) return rc;
-    } else if (plan.phase1_steps) {
-        if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, nullptr, s->cnt.ptr, &idx))) return rc;
-    } else if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) {
-        return rc;
+        if ((rc = dispatch_search_sweep(s, pb, plan, false, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
+    } else {
+        if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
+        if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) return rc;
     }
     return dispatch_sortback_counts(s, pb.n, idx, s->cnt.ptr, d_counts_out);
 }
@@ -728,17 +782,16 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
     uint64_t* offs_work = d_out_offs;  // small batch: work order == caller order
-    if (plan.sorted) {
+    const bool reordered = plan.sorted || plan.sweep;
+    if (reordered) {
         if ((rc = s->woffs.reserve((pb.n + 1) * 8))) return rc;
-        if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
     }
-    if (plan.sorted && plan.m1) {
-        if ((rc = dispatch_search_stream(s, pb, keys, plan.bits, plan.m1, s->sp.ptr, s->cnt.ptr))) return rc;
-    } else if (plan.sorted && plan.phase1_steps) {
-        if ((rc = dispatch_search_two_phase(s, pb, keys, idx, plan.bits, plan.phase1_steps, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
-    } else if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) {
-        return rc;
+    if (plan.sweep) {
+        if ((rc = dispatch_search_sweep(s, pb, plan, g_sweep_final_sort.load() != 0, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
+    } else {
+        if (plan.sorted && (rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
+        if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) return rc;
     }
     if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], offs_work + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
@@ -751,13 +804,13 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     *total_out = total;
     if ((rc = s->positions.reserve((total + 1) * P))) return rc;
     const bool by_position = (flags & SVFM_SORTED) != 0;
-    const bool records = plan.sorted || by_position;
+    const bool records = reordered || by_position;
     if (records && (rc = s->rec_key.reserve((total + 1) * 4))) return rc;
     *d_positions = s->positions.ptr;
     if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, offs_work, total, heavy_seen, s->positions.ptr,
                               records ? (uint32_t*)s->rec_key.ptr : nullptr)))
         return rc;
-    if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, plan.sorted, d_out_offs, d_positions))) return rc;
+    if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, reordered, d_out_offs, d_positions))) return rc;
     return SVFM_OK;
 }
 
@@ -788,7 +841,16 @@ static std::atomic<uint64_t> g_chunk_patterns{[] {
     const char* e = std::getenv("SVFM_CHUNK");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(16u << 20);
 }()};
-constexpr int HOST_WORKERS = 3;
+static std::atomic<uint64_t> g_host_workers{[] {
+    const char* e = std::getenv("SVFM_WORKERS");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)3;
+}()};
+static const bool g_trace = std::getenv("SVFM_TRACE") != nullptr;
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 __global__ void add_base_kernel(uint64_t* __restrict__ v, uint64_t n, uint64_t base) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] += base;
@@ -841,7 +903,8 @@ static int upload_chunk(svfm_session* s, const uint8_t* pats, const uint64_t* of
 
 template <class Fn>
 static int run_workers(svfm_index* ix, uint64_t chunks, Fn&& per_chunk) {
-    const int workers = (int)(chunks < (uint64_t)HOST_WORKERS ? chunks : (uint64_t)HOST_WORKERS);
+    const uint64_t hw = g_host_workers.load() ? g_host_workers.load() : 1;
+    const int workers = (int)(chunks < hw ? chunks : hw);
     std::atomic<uint64_t> next{0};
     std::atomic<int> first_err{SVFM_OK};
     std::string err_text;
@@ -916,6 +979,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
     std::vector<char> known(cp.chunks, 0);
     std::vector<void*> chunk_bufs(alloc_out ? cp.chunks : 0, nullptr);  // alloc mode: per-chunk pinned staging
     std::atomic<bool> overflow{false};
+    const double t_begin = g_trace ? now_ms() : 0;
     auto publish = [&](uint64_t c, uint64_t t) {
         std::lock_guard<std::mutex> g(mu);
         if (!known[c]) { totals[c] = t; known[c] = 1; }
@@ -926,11 +990,16 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         const uint64_t a = cp.begin(c), b = cp.end(c), m = b - a;
         PatternBatch pb;
         int r;
+        const double t_0 = g_trace ? now_ms() : 0;
         if ((r = upload_chunk(s, pats, offs, a, b, fixed_len, flags, pb))) return r;
+        if (g_trace) { cudaStreamSynchronize(s->stream); }
+        const double t_1 = g_trace ? now_ms() : 0;
         if ((r = s->out_offs.reserve((m + 1) * sizeof(uint64_t)))) return r;
         void* d_positions = nullptr;
         uint64_t total = 0;
         if ((r = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return r;
+        if (g_trace) { cudaStreamSynchronize(s->stream); }
+        const double t_2 = g_trace ? now_ms() : 0;
         publish(c, total);
         uint64_t base = 0;
         {
@@ -960,6 +1029,9 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
             }
         }
         SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        if (g_trace)
+            std::fprintf(stderr, "[svfm trace] chunk %llu n=%llu: start %.2f  h2d %.2f  kernels %.2f  d2h %.2f ms\n",
+                         (unsigned long long)c, (unsigned long long)m, t_0 - t_begin, t_1 - t_0, t_2 - t_1, now_ms() - t_2);
         return SVFM_OK;
     });
     uint64_t total = 0;
@@ -1037,6 +1109,7 @@ void svfm_free(svfm_index* ix) {
     cudaSetDevice(ix->device);
     for (svfm_session* s : ix->pool) session_delete(s);
     ix->pool.clear();
+    if (ix->d_ext) cudaFree(ix->d_ext);
     if (ix->d_alloc) cudaFree(ix->d_alloc);
     delete ix;
 }
@@ -1186,9 +1259,9 @@ int svfm_set_tuning(int key, uint64_t value) {
     switch (key) {
         case SVFM_TUNE_SORT_MIN: g_sort_min.store(value); return SVFM_OK;
         case SVFM_TUNE_CHUNK: g_chunk_patterns.store(value); return SVFM_OK;
-        case SVFM_TUNE_TWO_PHASE_MIN: g_two_phase_min.store(value); return SVFM_OK;
-        case SVFM_TUNE_STREAM_MIN: g_stream_min.store(value); return SVFM_OK;
-        case SVFM_TUNE_STREAM_STEPS: g_stream_steps.store(value); return SVFM_OK;
+        case SVFM_TUNE_SWEEP_MIN: g_sweep_min.store(value); return SVFM_OK;
+        case SVFM_TUNE_EXT_BITS: g_ext_bits.store(value); return SVFM_OK;
+        case SVFM_TUNE_WORKERS: g_host_workers.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -14,22 +14,24 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "readme_example.json")
 
 
-@pytest.fixture(scope="module", params=["sort_always", "sort_never", "sort_default"])
+@pytest.fixture(scope="module", params=["reorder_always", "reorder_never", "defaults", "no_ext_table"])
 def fm(request):
-    """Every parity test runs with the locality sort forced on, forced off and at its default threshold:
-    results must not depend on it."""
+    """Every parity test runs with the batch reordering (sweep search for fixed-length batches, locality sort for the
+    rest) forced on, forced off, at its default thresholds, and without the extended k-mer table (so that long
+    patterns seed from the blob's own kLTS): results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
-    value = {"sort_always": 0, "sort_never": 2**64 - 1, "sort_default": 1 << 17}[request.param]
-    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, value) == 0
-    # "sort_always" also forces the two-phase search (re-sort by SA position part-way) on every batch size
-    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 0 if request.param == "sort_always" else 2**64 - 1) == 0
-    # ... and the streaming search (suffix-sorted batch, seed + per-step kernels) on every fixed-length batch
-    assert _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_STREAM_MIN, 0 if request.param == "sort_always" else 2 << 20) == 0
+    L = _ffi.lib()
+    never = 2**64 - 1
+    sort_min, sweep_min, ext_bits = {"reorder_always": (0, 0, 24), "reorder_never": (never, never, 24),
+                                     "defaults": (1 << 17, 1 << 20, 24), "no_ext_table": (1 << 17, 0, 0)}[request.param]
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, ext_bits) == 0
     yield fm
-    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
-    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_TWO_PHASE_MIN, 2**64 - 1)
-    _ffi.lib().svfm_set_tuning(_ffi.SVFM_TUNE_STREAM_MIN, 2 << 20)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, 1 << 20)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, 24)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
@@ -97,6 +99,40 @@ def test_results_are_accurate(oracle, fm, chr_count):
             assert np.array_equal(pos[int(offs[i]):int(offs[i + 1])].astype(np.uint64), ans), (p, n, v, pat)
         _check_batch(ora, gpu, patterns[:40])
         gpu.close()
+
+
+def test_fixed_length_batches_every_type(oracle, fm):
+    """Fixed-length batches (the shape the sweep search takes) for every (P, Block, Vector): lengths below, at and
+    above the extended table's k, up to the longest pattern whose symbols fit the 64-bit item, and one beyond it;
+    patterns cut from the text, mutated, absent, and with the wildcard symbol."""
+    rng = np.random.default_rng(77)
+    for chr_count, with_wildcard in ((4, False), (4, True), (20, True), (50, False)):
+        chr_list = gen_rand_chr_list(rng, chr_count)
+        n = 6000
+        text = np.frombuffer(bytes(chr_list), dtype=np.uint8)[rng.integers(0, chr_count, size=n)].copy()
+        symbols = [bytes([c]) for c in chr_list]
+        if with_wildcard:
+            text[rng.integers(0, n, size=40)] = ord("~")  # not in any symbol set -> wildcard
+        for (p, nn, v) in ALL_TYPES:
+            if (1 << nn) < chr_count + (1 if with_wildcard else 0):
+                continue
+            if (p, v) not in ((32, 64), (64, 128), (64, 32)) and chr_count != 4:
+                continue  # all 30 types for DNA, a spread of them for the wider alphabets
+            ora, gpu, table, sc = _pair(oracle, fm, bytes(text), symbols, p, nn, v, 2, 3, with_wildcard=with_wildcard)
+            bits = max(1, int(np.ceil(np.log2(sc))))
+            for ln in (1, 3, 6, 7, 11, 64 // bits, 64 // bits + 7, 40):
+                m = 300
+                starts = rng.integers(0, n - ln, size=m)
+                pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
+                pats[::5, rng.integers(0, ln)] = chr_list[0]          # mutate: many become absent
+                pats[7::31, ln - 1] = ord("~")                        # wildcard / unmapped byte
+                oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
+                assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc), (p, nn, v, ln)
+                offs, pos = gpu.locate_batch(pats)
+                assert np.array_equal(offs, oo) and np.array_equal(pos.astype(np.uint64), op_.astype(np.uint64)), (p, nn, v, ln)
+                rc = gpu.count_batch(pats[:, ::-1], reversed_=True)
+                assert np.array_equal(rc.astype(np.uint64), oc), (p, nn, v, ln)
+            gpu.close()
 
 
 def test_config_invariance(oracle, fm):
