@@ -234,55 +234,115 @@ struct SweepPay { R rest; uint32_t idx; };
 template <class P>
 struct SweepVal { P sp; P cnt; uint32_t idx; };
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+constexpr int PACK_TILE = 256;    // patterns per tile (= threads per CTA)
+constexpr int PACK_STAGES = 4;    // tiles in flight per CTA
+
+// Encode + pack one fixed-length batch into sweep items.  The pattern bytes stream through shared memory in tiles of
+// PACK_TILE patterns, PACK_STAGES deep: one thread issues a TMA bulk copy per tile (cp.async.bulk, completion on an
+// mbarrier), every thread then packs its own pattern out of the staged tile.  Unaligned batches and the ragged last
+// tile take plain loads.
 template <class R>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(PACK_TILE)
 pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const PatternBatch pb, uint32_t bits, uint32_t m,
                   uint32_t* __restrict__ prefix, SweepPay<R>* __restrict__ pay, int* __restrict__ err) {
-    extern __shared__ __align__(16) uint8_t s_pats[];  // SEARCH_THREADS patterns
-    __shared__ uint8_t s_table[256];
-    __shared__ uint8_t s_rank[64];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = table ? table[i] : (uint8_t)i;
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = syms.sym_rank[i];
+    extern __shared__ __align__(128) uint8_t s_tiles[];  // PACK_STAGES x tile_bytes
+    __shared__ __align__(8) uint64_t s_bar[PACK_STAGES];
+    __shared__ uint16_t s_lut[256];                       // byte -> symbol index | rank << 8
     const uint32_t len = pb.fixed_len;
     const uint32_t S = syms.symbol_count;
+    const uint32_t tile_bytes = PACK_TILE * len;
+    const uint32_t stage_stride = (tile_bytes + 127u) & ~127u;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t sidx = table ? table[i] : (uint32_t)i;
+        const uint32_t bad = sidx >= S ? 0x8000u : 0u;     // PassThrough byte >= S
+        if (sidx >= S) sidx = S - 1;
+        s_lut[i] = (uint16_t)(sidx | ((uint32_t)(syms.sym_rank[sidx] & 0x7fu) << 8) | (syms.sym_rank[sidx] == 0xffu ? 0x4000u : 0u) | bad);
+    }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < PACK_STAGES; st++) mbar_init(&s_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t n_tiles = (pb.n + PACK_TILE - 1) / PACK_TILE;
+    const uint64_t full_tiles = pb.n / PACK_TILE;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(pb.pats) & 15u) == 0;  // tile_bytes = 256 * len is a multiple of 16
     int errbits = 0;
-    for (uint64_t i0 = (uint64_t)blockIdx.x * SEARCH_THREADS; i0 < pb.n; i0 += (uint64_t)gridDim.x * SEARCH_THREADS) {
-        const uint64_t cnt = pb.n - i0 < SEARCH_THREADS ? pb.n - i0 : SEARCH_THREADS;
-        const uint8_t* src = pb.pats + i0 * len;
-        const uint64_t bytes = cnt * len;
-        __syncthreads();
-        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            const uint64_t vec = bytes >> 4;
-            for (uint64_t o = threadIdx.x; o < vec; o += SEARCH_THREADS)
-                reinterpret_cast<uint4*>(s_pats)[o] = __ldg(reinterpret_cast<const uint4*>(src) + o);
-            for (uint64_t o = (vec << 4) + threadIdx.x; o < bytes; o += SEARCH_THREADS) s_pats[o] = __ldg(src + o);
-        } else {
-            for (uint64_t o = threadIdx.x; o < bytes; o += SEARCH_THREADS) s_pats[o] = __ldg(src + o);
-        }
-        __syncthreads();
-        if (threadIdx.x < cnt) {
-            const uint8_t* p = s_pats + (uint64_t)threadIdx.x * len;
-            uint32_t e = 0, mult = 1;
-            bool absent = false;
-            R rest = 0;
-            for (uint32_t j = 0; j < len; j++) {  // j-th symbol from the end
-                uint32_t s = s_table[p[pb.reversed ? j : len - 1 - j]];
-                if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
-                if (j < m) {
-                    const uint32_t r = s_rank[s];
-                    absent |= (r == 0xffu);
-                    e += r * mult;
-                    mult *= syms.s_eff;
-                } else {
-                    rest |= (R)s << (bits * (j - m));
-                }
+
+    auto pack_one = [&](const uint8_t* p, uint64_t i) {
+        uint32_t e = 0, mult = 1;
+        uint32_t flags = 0;
+        R rest = 0;
+        for (uint32_t j = 0; j < len; j++) {  // j-th symbol from the end
+            const uint32_t v = s_lut[p[pb.reversed ? j : len - 1 - j]];
+            flags |= v & 0x8000u;
+            if (j < m) {
+                flags |= v & 0x4000u;
+                e += ((v >> 8) & 0x3fu) * mult;
+                mult *= syms.s_eff;
+            } else {
+                rest |= (R)(v & 0xffu) << (bits * (j - m));
             }
-            prefix[i0 + threadIdx.x] = absent ? 0xffffffffu : e;
-            SweepPay<R> v;
-            v.rest = rest;
-            v.idx = (uint32_t)(i0 + threadIdx.x);
-            pay[i0 + threadIdx.x] = v;
         }
+        if (flags & 0x8000u) errbits |= ERRBIT_BAD_SYMBOL;
+        prefix[i] = (flags & 0x4000u) ? 0xffffffffu : e;
+        SweepPay<R> o;
+        o.rest = rest;
+        o.idx = (uint32_t)i;
+        pay[i] = o;
+    };
+
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_of = [&](uint64_t it) { return (uint64_t)blockIdx.x + it * gridDim.x; };
+    auto issue = [&](uint64_t it) {  // thread 0 only
+        const uint64_t t = tile_of(it);
+        if (it < my_tiles && t < full_tiles && tma_ok) {
+            uint64_t* bar = &s_bar[it % PACK_STAGES];
+            mbar_expect_tx(bar, tile_bytes);
+            bulk_g2s(s_tiles + (it % PACK_STAGES) * (uint64_t)stage_stride, pb.pats + t * (uint64_t)tile_bytes, tile_bytes, bar);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (uint64_t it = 0; it + 1 < PACK_STAGES; it++) issue(it);
+    for (uint64_t it = 0; it < my_tiles; it++) {
+        const uint64_t t = tile_of(it);
+        const uint64_t i0 = t * PACK_TILE;
+        uint8_t* stage = s_tiles + (it % PACK_STAGES) * (uint64_t)stage_stride;
+        // every thread is past iteration it-1 here (barrier at its end), so stage (it-1) % STAGES may be refilled
+        if (threadIdx.x == 0) issue(it + PACK_STAGES - 1);
+        if (t < full_tiles && tma_ok) {
+            mbar_wait(&s_bar[it % PACK_STAGES], (uint32_t)((it / PACK_STAGES) & 1));
+        } else {
+            const uint64_t cnt = pb.n - i0 < PACK_TILE ? pb.n - i0 : PACK_TILE;
+            const uint8_t* src = pb.pats + i0 * len;
+            for (uint64_t o = threadIdx.x; o < cnt * len; o += PACK_TILE) stage[o] = __ldg(src + o);
+            __syncthreads();
+        }
+        if (i0 + threadIdx.x < pb.n) pack_one(stage + (uint64_t)threadIdx.x * len, i0 + threadIdx.x);
+        __syncthreads();
     }
     if (errbits) atomicOr(err, errbits);
 }

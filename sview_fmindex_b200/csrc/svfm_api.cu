@@ -32,6 +32,8 @@ std::atomic<uint64_t> g_launches{0};
 // ---------------------------------------------------------------------------------------------
 }  // namespace svfm
 
+struct svfm_uploader;
+
 struct svfm_index {
     svfm_type type;
     svfm::Layout L;
@@ -49,12 +51,21 @@ struct svfm_index {
     void* d_ext = nullptr;         // P[2 * ext_entries]
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
+    std::vector<svfm_uploader*> up_pool;  // idle uploaders
+};
+
+// Upload side of the host-buffer entry points: ONE stream keeps the host->device copy engine busy with the chunks
+// of a batch back to back, into one device buffer; the worker sessions wait on a per-chunk event.
+struct svfm_uploader {
+    cudaStream_t stream = nullptr;
+    svfm::DeviceBuffer pats, offs;
+    std::vector<cudaEvent_t> ev;
 };
 
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
     svfm::DeviceBuffer pay0, pay1, rest0, rest1, val0, val1; // sweep search: items moving through the radix partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
@@ -508,9 +519,14 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
         syms.symbol_count = ix->L.symbol_count;
         syms.s_eff = ix->symbols_present;
         std::memcpy(syms.sym_rank, ix->sym_rank, 64);
-        const size_t smem = ((size_t)SEARCH_THREADS * len + 15) & ~(size_t)15;
-        int grid = grid_for(n, SEARCH_THREADS, ix->device);
-        pack_sweep_kernel<R><<<grid, SEARCH_THREADS, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(), s->d_err);
+        const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127);
+        SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;
+        if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
+        pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(), s->d_err);
         SVFM_CUDA(cudaGetLastError());
         SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
     }
@@ -869,43 +885,152 @@ static ChunkPlan plan_chunks(uint64_t n) {
     if (c == 0) c = n;
     p.chunks = (n + c - 1) / c;
     if (p.chunks == 0) p.chunks = 1;
-    p.chunk = (n + p.chunks - 1) / p.chunks;  // even chunks
+    p.chunk = (n + p.chunks - 1) / p.chunks;  // even chunks ...
+    if (p.chunks > 1) p.chunk = (p.chunk + 255) & ~(uint64_t)255;  // ... whose device copies stay 16-byte aligned (TMA staging)
     if (p.chunk == 0) p.chunk = 1;
     p.chunks = (n + p.chunk - 1) / p.chunk;
     if (p.chunks == 0) p.chunks = 1;
     return p;
 }
 
-// Upload patterns [a, b) of a host batch into the session's arena.
-static int upload_chunk(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t a, uint64_t b,
-                        uint32_t fixed_len, uint32_t flags, PatternBatch& pb) {
-    int rc;
-    pb.n = b - a;
-    pb.fixed_len = fixed_len;
-    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
-    pb.offs = nullptr;
-    if (!offs) {
-        const uint64_t bytes = (b - a) * (uint64_t)fixed_len;
-        if ((rc = s->pats.reserve(bytes + 16))) return rc;
-        SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + a * (uint64_t)fixed_len, bytes, cudaMemcpyHostToDevice, s->stream));
-        pb.pats = (const uint8_t*)s->pats.ptr;
+static std::atomic<uint64_t> g_upload_budget{[] {  // device bytes of pattern staging per host call
+    const char* e = std::getenv("SVFM_UPLOAD_BUDGET");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)8 << 30;
+}()};
+
+struct UploaderLease {
+    svfm_index* ix;
+    svfm_uploader* u = nullptr;
+    explicit UploaderLease(svfm_index* i) : ix(i) {}
+    int acquire() {
+        {
+            std::lock_guard<std::mutex> g(ix->pool_mu);
+            if (!ix->up_pool.empty()) { u = ix->up_pool.back(); ix->up_pool.pop_back(); }
+        }
+        SVFM_CUDA(cudaSetDevice(ix->device));
+        if (u) return SVFM_OK;
+        u = new svfm_uploader();
+        cudaError_t e = cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete u; u = nullptr; SVFM_CUDA(e); }
         return SVFM_OK;
     }
-    const uint64_t base = offs[a], bytes = offs[b] - base;
-    if ((rc = s->pats.reserve(bytes + 16))) return rc;
-    if ((rc = s->offs.reserve((b - a + 1) * sizeof(uint64_t)))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + base, bytes, cudaMemcpyHostToDevice, s->stream));
-    SVFM_CUDA(cudaMemcpyAsync(s->offs.ptr, offs + a, (b - a + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
-    pb.pats = (const uint8_t*)s->pats.ptr - base;  // offsets stay absolute
-    pb.offs = (const uint64_t*)s->offs.ptr;
+    ~UploaderLease() {
+        if (u) { std::lock_guard<std::mutex> g(ix->pool_mu); ix->up_pool.push_back(u); }
+    }
+};
+
+// One group of consecutive chunks [g0, g1) of a host batch whose pattern bytes fit the staging budget.
+struct UploadGroup {
+    svfm_uploader* u = nullptr;
+    const uint8_t* pats = nullptr;
+    const uint64_t* offs = nullptr;
+    uint32_t fixed_len = 0, flags = 0;
+    uint64_t g0 = 0, g1 = 0, first_pattern = 0, first_byte = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t issued = 0;  // chunks of this group whose copies are enqueued (events recorded)
+    int rc = SVFM_OK;
+};
+
+static uint64_t chunk_bytes(const ChunkPlan& cp, const uint64_t* offs, uint32_t fixed_len, uint64_t c) {
+    const uint64_t a = cp.begin(c), b = cp.end(c);
+    return offs ? offs[b] - offs[a] : (b - a) * (uint64_t)fixed_len;
+}
+
+// Enqueue the copies of every chunk of the group on the uploader's stream (called by one host thread while the
+// workers already consume the first chunks).
+static void upload_group(const ChunkPlan& cp, UploadGroup& g) {
+    svfm_uploader* u = g.u;
+    for (uint64_t c = g.g0; c < g.g1; c++) {
+        const uint64_t a = cp.begin(c), b = cp.end(c);
+        cudaError_t e;
+        if (!g.offs) {
+            e = cudaMemcpyAsync((uint8_t*)u->pats.ptr + (a - g.first_pattern) * (uint64_t)g.fixed_len, g.pats + a * (uint64_t)g.fixed_len,
+                                (b - a) * (uint64_t)g.fixed_len, cudaMemcpyHostToDevice, u->stream);
+        } else {
+            e = cudaMemcpyAsync((uint8_t*)u->pats.ptr + (g.offs[a] - g.first_byte), g.pats + g.offs[a], g.offs[b] - g.offs[a],
+                                cudaMemcpyHostToDevice, u->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((uint64_t*)u->offs.ptr + (a - g.first_pattern), g.offs + a, (b - a + 1) * sizeof(uint64_t),
+                                    cudaMemcpyHostToDevice, u->stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(u->ev[c - g.g0], u->stream);
+        std::lock_guard<std::mutex> lk(g.mu);
+        if (e != cudaSuccess) {
+            g_last_error = std::string("upload: ") + cudaGetErrorString(e);
+            g.rc = SVFM_ERR_CUDA;
+            g.issued = g.g1 - g.g0;  // nobody may wait forever
+            g.cv.notify_all();
+            return;
+        }
+        g.issued = c - g.g0 + 1;
+        g.cv.notify_all();
+    }
+}
+
+// Worker side: make the session's stream wait for chunk c of the group and describe it as a PatternBatch.
+static int await_chunk(svfm_session* s, const ChunkPlan& cp, UploadGroup& g, uint64_t c, PatternBatch& pb) {
+    {
+        std::unique_lock<std::mutex> lk(g.mu);
+        g.cv.wait(lk, [&] { return g.issued > c - g.g0; });
+        if (g.rc) return g.rc;
+    }
+    SVFM_CUDA(cudaStreamWaitEvent(s->stream, g.u->ev[c - g.g0], 0));
+    const uint64_t a = cp.begin(c), b = cp.end(c);
+    pb.n = b - a;
+    pb.fixed_len = g.fixed_len;
+    pb.reversed = (g.flags & SVFM_REVERSED) ? 1u : 0u;
+    if (!g.offs) {
+        pb.pats = (const uint8_t*)g.u->pats.ptr + (a - g.first_pattern) * (uint64_t)g.fixed_len;
+        pb.offs = nullptr;
+    } else {
+        pb.pats = (const uint8_t*)g.u->pats.ptr - g.first_byte;  // offsets stay absolute
+        pb.offs = (const uint64_t*)g.u->offs.ptr + (a - g.first_pattern);
+    }
     return SVFM_OK;
 }
 
-template <class Fn>
-static int run_workers(svfm_index* ix, uint64_t chunks, Fn&& per_chunk) {
+// Next group of chunks starting at g0: reserve its staging and events.
+static int begin_group(svfm_uploader* u, const ChunkPlan& cp, const uint8_t* pats, const uint64_t* offs, uint32_t fixed_len,
+                       uint32_t flags, uint64_t g0, UploadGroup& g) {
+    const uint64_t budget = g_upload_budget.load();
+    uint64_t g1 = g0, bytes = 0;
+    while (g1 < cp.chunks) {
+        const uint64_t cb = chunk_bytes(cp, offs, fixed_len, g1);
+        if (g1 > g0 && bytes + cb > budget) break;
+        bytes += cb;
+        g1++;
+    }
+    g.u = u;
+    g.pats = pats;
+    g.offs = offs;
+    g.fixed_len = fixed_len;
+    g.flags = flags;
+    g.g0 = g0;
+    g.g1 = g1;
+    g.first_pattern = cp.begin(g0);
+    g.first_byte = offs ? offs[g.first_pattern] : g.first_pattern * (uint64_t)fixed_len;
+    g.issued = 0;
+    g.rc = SVFM_OK;
+    int rc;
+    if ((rc = u->pats.reserve(bytes + 256))) return rc;
+    if (offs && (rc = u->offs.reserve((cp.end(g1 - 1) - g.first_pattern + 1) * sizeof(uint64_t)))) return rc;
+    while (u->ev.size() < g1 - g0) {
+        cudaEvent_t e;
+        SVFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        u->ev.push_back(e);
+    }
+    return SVFM_OK;
+}
+
+// per_chunk(session, c) for c in [c0, c1) over up to `workers` sessions; `prologue` runs on the calling thread before it
+// turns into a worker itself.
+template <class Fn, class Pro>
+static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, Fn&& per_chunk, Pro&& prologue) {
+    const uint64_t chunks = c1 - c0;
     const uint64_t hw = g_host_workers.load() ? g_host_workers.load() : 1;
     const int workers = (int)(chunks < hw ? chunks : hw);
-    std::atomic<uint64_t> next{0};
+    std::atomic<uint64_t> next{c0};
     std::atomic<int> first_err{SVFM_OK};
     std::string err_text;
     std::mutex err_mu;
@@ -914,7 +1039,7 @@ static int run_workers(svfm_index* ix, uint64_t chunks, Fn&& per_chunk) {
         int rc = lease.acquire();
         for (;;) {
             const uint64_t c = next.fetch_add(1);
-            if (c >= chunks) break;
+            if (c >= c1) break;
             const bool run = (rc == SVFM_OK && first_err.load() == SVFM_OK);
             if (run) rc = per_chunk(lease.s, c);
             if (rc != SVFM_OK) {
@@ -929,10 +1054,12 @@ static int run_workers(svfm_index* ix, uint64_t chunks, Fn&& per_chunk) {
         if (lease.s) cudaStreamSynchronize(lease.s->stream);
     };
     if (workers <= 1) {
+        prologue();
         body();
     } else {
         std::vector<std::thread> th;
         for (int t = 1; t < workers; t++) th.emplace_back(body);
+        prologue();
         body();
         for (auto& t : th) t.join();
     }
@@ -944,19 +1071,30 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
                       uint32_t flags, void* counts_out) {
     const uint64_t P = ix->type.pos_bits / 8;
     const ChunkPlan cp = plan_chunks(n);
-    return run_workers(ix, cp.chunks, [&](svfm_session* s, uint64_t c) -> int {
-        if (!s) return SVFM_OK;
-        const uint64_t a = cp.begin(c), b = cp.end(c);
-        PatternBatch pb;
-        int rc;
-        if ((rc = upload_chunk(s, pats, offs, a, b, fixed_len, flags, pb))) return rc;
-        if ((rc = s->counts_out.reserve((b - a) * P))) return rc;  // not s->cnt: count_device uses that in work order
-        if ((rc = count_device(s, pb, s->counts_out.ptr))) return rc;
-        SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
-        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        SVFM_CUDA(cudaStreamSynchronize(s->stream));
-        return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
-    });
+    UploaderLease up(ix);
+    int rc = up.acquire();
+    if (rc) return rc;
+    for (uint64_t g0 = 0; g0 < cp.chunks;) {
+        UploadGroup g;
+        if ((rc = begin_group(up.u, cp, pats, offs, fixed_len, flags, g0, g))) return rc;
+        rc = run_workers(ix, g.g0, g.g1, [&](svfm_session* s, uint64_t c) -> int {
+            if (!s) return SVFM_OK;
+            const uint64_t a = cp.begin(c), b = cp.end(c);
+            PatternBatch pb;
+            int r;
+            if ((r = await_chunk(s, cp, g, c, pb))) return r;
+            if ((r = s->counts_out.reserve((b - a) * P))) return r;  // not s->cnt: count_device uses that in work order
+            if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
+            SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
+            SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            SVFM_CUDA(cudaStreamSynchronize(s->stream));
+            return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
+        }, [&] { upload_group(cp, g); });
+        cudaStreamSynchronize(up.u->stream);
+        if (rc) return rc;
+        g0 = g.g1;
+    }
+    return SVFM_OK;
 }
 
 static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
@@ -985,13 +1123,19 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         if (!known[c]) { totals[c] = t; known[c] = 1; }
         cv.notify_all();
     };
-    rc = run_workers(ix, cp.chunks, [&](svfm_session* s, uint64_t c) -> int {
+    UploaderLease up(ix);
+    if ((rc = up.acquire())) return rc;
+    for (uint64_t g0 = 0; g0 < cp.chunks && rc == SVFM_OK;) {
+    UploadGroup g;
+    if ((rc = begin_group(up.u, cp, pats, offs, fixed_len, flags, g0, g))) break;
+    g0 = g.g1;
+    rc = run_workers(ix, g.g0, g.g1, [&](svfm_session* s, uint64_t c) -> int {
         if (!s) { publish(c, 0); return SVFM_OK; }
         const uint64_t a = cp.begin(c), b = cp.end(c), m = b - a;
         PatternBatch pb;
         int r;
         const double t_0 = g_trace ? now_ms() : 0;
-        if ((r = upload_chunk(s, pats, offs, a, b, fixed_len, flags, pb))) return r;
+        if ((r = await_chunk(s, cp, g, c, pb))) return r;
         if (g_trace) { cudaStreamSynchronize(s->stream); }
         const double t_1 = g_trace ? now_ms() : 0;
         if ((r = s->out_offs.reserve((m + 1) * sizeof(uint64_t)))) return r;
@@ -1033,7 +1177,9 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
             std::fprintf(stderr, "[svfm trace] chunk %llu n=%llu: start %.2f  h2d %.2f  kernels %.2f  d2h %.2f ms\n",
                          (unsigned long long)c, (unsigned long long)m, t_0 - t_begin, t_1 - t_0, t_2 - t_1, now_ms() - t_2);
         return SVFM_OK;
-    });
+    }, [&] { upload_group(cp, g); });
+    cudaStreamSynchronize(up.u->stream);
+    }
     uint64_t total = 0;
     for (uint64_t c = 0; c < cp.chunks; c++) total += totals[c];
     *total_out = total;
@@ -1109,6 +1255,12 @@ void svfm_free(svfm_index* ix) {
     cudaSetDevice(ix->device);
     for (svfm_session* s : ix->pool) session_delete(s);
     ix->pool.clear();
+    for (svfm_uploader* u : ix->up_pool) {
+        if (u->stream) { cudaStreamSynchronize(u->stream); cudaStreamDestroy(u->stream); }
+        for (cudaEvent_t e : u->ev) cudaEventDestroy(e);
+        delete u;
+    }
+    ix->up_pool.clear();
     if (ix->d_ext) cudaFree(ix->d_ext);
     if (ix->d_alloc) cudaFree(ix->d_alloc);
     delete ix;
