@@ -154,7 +154,6 @@ enum {
     SVFM_PHASE_LOCATE = 3,  /* LF-walk + sampled-SA lookup kernel */
     SVFM_PHASE_SEGSORT = 4, /* optional per-pattern sort of the positions (SVFM_SORTED) */
     SVFM_PHASE_OTHER = 5,   /* back to the caller's order: radix sort by pattern index, CSR offsets */
-    SVFM_PHASE_PARTITION = 6, /* sweep search: radix partition of the batch between rounds of backward steps */
     SVFM_PHASE_MAX = 8
 };
 int svfm_session_set_timing(svfm_session* s, int enabled);

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvfm.so")
+LIB_PATH = os.environ.get("SVFM_LIB_PATH") or os.path.join(_HERE, "libsvfm.so")  # override: developer builds only
 
 SVFM_OK = 0
 SVFM_ERR_INVALID_FORMAT = 1

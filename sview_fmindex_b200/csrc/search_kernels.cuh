@@ -231,8 +231,6 @@ ext_expand_kernel(const DevIndex<P> ix, const P* __restrict__ in, uint64_t n_in,
 // streams instead of random sectors (measured on B200: 55 G random sectors/s = 1.76 TB/s vs 6.5 TB/s streaming).
 template <class R>
 struct SweepPay { R rest; uint32_t idx; };
-template <class P>
-struct SweepVal { P sp; P cnt; uint32_t idx; };
 
 // ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier) --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -267,14 +265,19 @@ constexpr int PACK_STAGES = 4;    // tiles in flight per CTA
 template <class R>
 __global__ void __launch_bounds__(PACK_TILE)
 pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const PatternBatch pb, uint32_t bits, uint32_t m,
-                  uint32_t* __restrict__ prefix, SweepPay<R>* __restrict__ pay, int* __restrict__ err) {
-    extern __shared__ __align__(128) uint8_t s_tiles[];  // PACK_STAGES x tile_bytes
+                  uint32_t* __restrict__ prefix, SweepPay<R>* __restrict__ pay, uint32_t digit_bits, uint32_t n_rounds,
+                  uint32_t* __restrict__ hist, int* __restrict__ err) {
+    extern __shared__ __align__(128) uint8_t s_tiles[];  // PACK_STAGES x tile_bytes | round histograms
     __shared__ __align__(8) uint64_t s_bar[PACK_STAGES];
     __shared__ uint16_t s_lut[256];                       // byte -> symbol index | rank << 8
     const uint32_t len = pb.fixed_len;
     const uint32_t S = syms.symbol_count;
     const uint32_t tile_bytes = PACK_TILE * len;
     const uint32_t stage_stride = (tile_bytes + 127u) & ~127u;
+    // digit histograms of the partition rounds (sweep_round_kernel): round r sorts on bits [r*digit_bits, +digit_bits) of rest
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_tiles + (size_t)PACK_STAGES * stage_stride);
+    const uint32_t nb = 1u << digit_bits;
+    for (uint32_t i = threadIdx.x; i < n_rounds * nb; i += blockDim.x) s_hist[i] = 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t sidx = table ? table[i] : (uint32_t)i;
         const uint32_t bad = sidx >= S ? 0x8000u : 0u;     // PassThrough byte >= S
@@ -308,6 +311,7 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
         }
         if (flags & 0x8000u) errbits |= ERRBIT_BAD_SYMBOL;
         prefix[i] = (flags & 0x4000u) ? 0xffffffffu : e;
+        for (uint32_t r = 0; r < n_rounds; r++) atomicAdd(&s_hist[r * nb + (uint32_t)((rest >> (r * digit_bits)) & (R)(nb - 1))], 1u);
         SweepPay<R> o;
         o.rest = rest;
         o.idx = (uint32_t)i;
@@ -344,87 +348,256 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
         if (i0 + threadIdx.x < pb.n) pack_one(stage + (uint64_t)threadIdx.x * len, i0 + threadIdx.x);
         __syncthreads();
     }
+    for (uint32_t i = threadIdx.x; i < n_rounds * nb; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
     if (errbits) atomicOr(err, errbits);
 }
 
+// State of one pattern between rounds.  16 bytes for u32 positions and <= 32 bits of remaining symbols (one
+// LDG.128 / STG.128 per item), 24 or 32 bytes otherwise.
 template <class P, class R>
-struct SweepIO {
-    // FIRST round: items as sorted by prefix
+struct alignas((2 * sizeof(P) + sizeof(R) + 4) % 16 == 0 ? 16 : 8) SweepItem {
+    P sp;
+    P cnt;
+    R rest;
+    uint32_t idx;
+};
+
+constexpr int ROUND_THREADS = 256;
+#ifndef SVFM_ROUND_ITEMS
+#define SVFM_ROUND_ITEMS 4
+#endif
+#ifndef SVFM_ROUND_MIN_CTAS
+#define SVFM_ROUND_MIN_CTAS 5
+#endif
+constexpr int ROUND_ITEMS = SVFM_ROUND_ITEMS;               // items per thread
+constexpr int ROUND_TILE = ROUND_THREADS * ROUND_ITEMS;     // items per tile
+constexpr int ROUND_WARPS = ROUND_THREADS / 32;
+constexpr int ROUND_MAX_BINS = 512;
+constexpr uint32_t DESC_AGG = 1u << 30, DESC_PREFIX = 2u << 30, DESC_MASK = (1u << 30) - 1;
+
+template <class P, class R>
+struct SweepRoundIO {
+    // FIRST round: items as radix-sorted by prefix
     const uint32_t* prefix;
     const SweepPay<R>* pay;
     // later rounds: items as partitioned by the previous round
-    const R* rest_in;
-    const SweepVal<P>* val_in;
-    // outputs (each nullable): state for the next partition / round, or the final work-order arrays
-    R* rest_out;
-    SweepVal<P>* val_out;
+    const SweepItem<P, R>* items_in;
+    // outputs (each nullable), written at the partitioned position (PART) or in place
+    SweepItem<P, R>* items_out;
     P* sp_out;
     P* cnt_out;
     uint32_t* idx_out;
+    // PART only
+    const uint32_t* hist;      // digit histogram of this round over the whole batch (pack_sweep_kernel), nbins entries
+    uint32_t* desc;            // tiles x nbins look-back descriptors, zeroed before the launch
+    uint32_t* tile_counter;    // zeroed before the launch
     unsigned long long* heavy_seen;
 };
 
-// One round: seed from the extended table (FIRST) or resume, then `steps` backward steps consuming the symbols at
-// bit offset `shift`, `shift + bits`, ... of `rest`.
-template <class P, int NPL, int VBITS, class R, bool FIRST>
-__global__ void __launch_bounds__(SEARCH_THREADS)
-sweep_step_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shift, uint32_t steps, const SweepIO<P, R> io) {
-    __shared__ P s_count[65];
-    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
-    __syncthreads();
-    const R sym_mask = (R)((1ull << bits) - 1);
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
-        R rest;
-        uint32_t idx;
-        P sp = 0, cnt = 0;
-        if (FIRST) {
-            const uint32_t e = io.prefix[w];
-            const SweepPay<R> v = io.pay[w];
-            rest = v.rest;
-            idx = v.idx;
-            if (e != 0xffffffffu) {
-                const P* q = ix.ext + 2 * (uint64_t)e;
-                sp = __ldg(q);
-                cnt = __ldg(q + 1);
-            }
-        } else {
-            rest = io.rest_in[w];
-            const SweepVal<P> v = io.val_in[w];
-            sp = v.sp;
-            cnt = v.cnt;
-            idx = v.idx;
-        }
-        if (cnt != 0) {
-            P ep = (P)(sp + cnt);
-            for (uint32_t t = 0; t < steps && sp < ep; t++)
-                backward_step<P, NPL, VBITS>(ix, s_count, (uint32_t)((rest >> (shift + bits * t)) & sym_mask), sp, ep);
-            cnt = (P)(ep - sp);
-        }
-        if (io.rest_out) io.rest_out[w] = rest;
-        if (io.val_out) {
-            SweepVal<P> v;
-            v.sp = sp;
-            v.cnt = cnt;
-            v.idx = idx;
-            io.val_out[w] = v;
-        }
-        if (io.sp_out) io.sp_out[w] = sp;
-        if (io.cnt_out) io.cnt_out[w] = cnt;
-        if (io.idx_out) io.idx_out[w] = idx;
-        if (io.heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);
-    }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Final partition output (array of structs) -> the work-order arrays scan / locate / sort-back read.
-template <class P>
-__global__ void __launch_bounds__(SEARCH_THREADS)
-sweep_unzip_kernel(const SweepVal<P>* __restrict__ val, uint64_t n, P* __restrict__ sp_out, P* __restrict__ cnt_out,
-                   uint32_t* __restrict__ idx_out) {
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
-        const SweepVal<P> v = val[w];
-        sp_out[w] = v.sp;
-        cnt_out[w] = v.cnt;
-        idx_out[w] = v.idx;
+// One round of the sweep search, fused with the radix partition that follows it (PART):
+//   load a tile of items (FIRST: seed them from the extended table) -> `steps` backward steps each
+//   (with_slice.rs:27-31) -> digit = the symbols just consumed, last one most significant -> stable rank of every
+//   item inside its digit (warp match + per-warp counters) -> exclusive prefix of the digit counts over all earlier
+//   tiles by decoupled look-back (one descriptor word per tile and digit: flag | count) -> items leave through a
+//   shared-memory exchange so that every digit's run is written with coalesced stores.
+// Tiles are handed out by an atomic counter, so a tile's predecessors are always running or done.
+// Without PART (last round of `count`) items are written back in place.
+template <class P, int NPL, int VBITS, class R, bool FIRST, bool PART>
+__global__ void __launch_bounds__(ROUND_THREADS, SVFM_ROUND_MIN_CTAS)
+sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shift, uint32_t steps, uint32_t nbins,
+                   const SweepRoundIO<P, R> io) {
+    using Item = SweepItem<P, R>;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ P s_count[65];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_scan[ROUND_WARPS];
+    // dynamic: items[ROUND_TILE] | whist[ROUND_WARPS][nbins] | binstart[nbins] | tilebin[nbins] | gbase[nbins] (u64)
+    Item* s_items = reinterpret_cast<Item*>(s_dyn);
+    uint64_t* s_gbase = reinterpret_cast<uint64_t*>(s_dyn + sizeof(Item) * ROUND_TILE);
+    uint64_t* s_binstart = s_gbase + nbins;
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_binstart + nbins);
+    uint32_t* s_tilebin = s_whist + ROUND_WARPS * nbins;
+
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    if (PART) {
+        // global start of every digit = exclusive scan of the batch histogram (serial per warp-chunk; nbins <= 512)
+        if (threadIdx.x == 0) {
+            uint64_t acc = 0;
+            for (uint32_t b = 0; b < nbins; b++) { s_binstart[b] = acc; acc += io.hist[b]; }
+        }
+    }
+    __syncthreads();
+    const R sym_mask = (R)((1ull << bits) - 1);
+    const R digit_mask = (R)(nbins - 1);
+    const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(io.tile_counter, 1u);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        __syncthreads();  // everyone has read s_tile before thread 0 can overwrite it
+        if (tile >= n_tiles) break;
+        const uint64_t base = tile * ROUND_TILE + (uint64_t)warp * (32 * ROUND_ITEMS) + lane;
+        P sp[ROUND_ITEMS], cnt[ROUND_ITEMS];
+        R rest[ROUND_ITEMS];
+        uint32_t idx[ROUND_ITEMS];
+        // ---- load (warp-striped: row k of a warp is 32 consecutive items)
+#pragma unroll
+        for (int k = 0; k < ROUND_ITEMS; k++) {
+            const uint64_t w = base + (uint64_t)k * 32;
+            sp[k] = 0; cnt[k] = 0; rest[k] = 0; idx[k] = 0;
+            if (w < n) {
+                if (FIRST) {
+                    const uint32_t e = io.prefix[w];
+                    const SweepPay<R> v = io.pay[w];
+                    rest[k] = v.rest;
+                    idx[k] = v.idx;
+                    if (e != 0xffffffffu) {
+                        const P* q = ix.ext + 2 * (uint64_t)e;
+                        sp[k] = __ldg(q);
+                        cnt[k] = __ldg(q + 1);
+                    }
+                } else {
+                    const Item v = io.items_in[w];
+                    sp[k] = v.sp; cnt[k] = v.cnt; rest[k] = v.rest; idx[k] = v.idx;
+                }
+            }
+        }
+        // ---- stable rank inside the tile.  The digit depends on the pattern alone, so the tile's digit counts are
+        // published BEFORE the backward steps: by the time this tile looks back, its predecessors have long done so too.
+        uint32_t rank[ROUND_ITEMS], dig[ROUND_ITEMS];
+        uint32_t* my_hist = s_whist + warp * nbins;
+        if constexpr (PART) {
+            for (uint32_t i = threadIdx.x; i < ROUND_WARPS * nbins; i += ROUND_THREADS) s_whist[i] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < ROUND_ITEMS; k++) {
+                const bool valid = base + (uint64_t)k * 32 < n;
+                dig[k] = valid ? (uint32_t)((rest[k] >> shift) & digit_mask) : 0xffffffffu;
+                const unsigned peers = __match_any_sync(full, dig[k]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t before = 0;
+                if ((int)lane == leader && valid) {
+                    before = my_hist[dig[k]];
+                    my_hist[dig[k]] = before + __popc(peers);
+                }
+                before = __shfl_sync(full, before, leader);
+                rank[k] = before + __popc(peers & ((1u << lane) - 1u));
+                __syncwarp();
+            }
+            __syncthreads();
+            // per digit: offsets of the warps inside the tile, tile total -> descriptor (aggregate)
+            for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+                uint32_t acc = 0;
+                for (int w = 0; w < ROUND_WARPS; w++) {
+                    const uint32_t t = s_whist[w * nbins + b];
+                    s_whist[w * nbins + b] = acc;
+                    acc += t;
+                }
+                s_tilebin[b] = acc;
+                st_volatile_u32(io.desc + tile * nbins + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+            }
+        }
+        // ---- backward steps
+#pragma unroll
+        for (int k = 0; k < ROUND_ITEMS; k++) {
+            if (cnt[k] != 0) {
+                P ep = (P)(sp[k] + cnt[k]);
+                for (uint32_t t = 0; t < steps && sp[k] < ep; t++)
+                    backward_step<P, NPL, VBITS>(ix, s_count, (uint32_t)((rest[k] >> (shift + bits * t)) & sym_mask), sp[k], ep);
+                cnt[k] = (P)(ep - sp[k]);
+            }
+            if (io.heavy_seen && (uint64_t)cnt[k] > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);
+        }
+        if constexpr (!PART) {
+#pragma unroll
+            for (int k = 0; k < ROUND_ITEMS; k++) {
+                const uint64_t w = base + (uint64_t)k * 32;
+                if (w < n) {
+                    if (io.items_out) { Item v; v.sp = sp[k]; v.cnt = cnt[k]; v.rest = rest[k]; v.idx = idx[k]; io.items_out[w] = v; }
+                    if (io.sp_out) io.sp_out[w] = sp[k];
+                    if (io.cnt_out) io.cnt_out[w] = cnt[k];
+                    if (io.idx_out) io.idx_out[w] = idx[k];
+                }
+            }
+        } else {
+        // ---- look-back over the earlier tiles (decoupled: aggregate or inclusive prefix per tile and digit)
+        for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+            uint32_t excl = 0;
+            const uint32_t acc = s_tilebin[b];
+            if (tile > 0) {
+                for (uint64_t t = tile - 1;; t--) {
+                    uint32_t v;
+                    do { v = ld_volatile_u32(io.desc + t * nbins + b); } while ((v >> 30) == 0);
+                    excl += v & DESC_MASK;
+                    if ((v >> 30) == 2u || t == 0) break;
+                }
+                st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + acc));
+            }
+            s_gbase[b] = s_binstart[b] + excl;
+        }
+        __syncthreads();
+        // exclusive scan of the tile totals over the digits (position of every digit's run inside the exchange buffer)
+        {
+            uint32_t v[ROUND_MAX_BINS / ROUND_THREADS], sum = 0;
+#pragma unroll
+            for (int i = 0; i < ROUND_MAX_BINS / ROUND_THREADS; i++) {
+                const uint32_t b = threadIdx.x * (ROUND_MAX_BINS / ROUND_THREADS) + i;
+                v[i] = b < nbins ? s_tilebin[b] : 0u;
+                sum += v[i];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t o = __shfl_up_sync(full, incl, dlt);
+                if ((int)lane >= dlt) incl += o;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off = 0;
+            for (uint32_t w = 0; w < warp; w++) warp_off += s_scan[w];
+            uint32_t run = warp_off + incl - sum;
+#pragma unroll
+            for (int i = 0; i < ROUND_MAX_BINS / ROUND_THREADS; i++) {
+                const uint32_t b = threadIdx.x * (ROUND_MAX_BINS / ROUND_THREADS) + i;
+                if (b < nbins) { s_tilebin[b] = run; s_gbase[b] -= run; }  // global position = gbase[digit] + slot in the buffer
+                run += v[i];
+            }
+        }
+        __syncthreads();
+        // ---- exchange through shared memory: slot = run start of the digit + warps before me + rank
+#pragma unroll
+        for (int k = 0; k < ROUND_ITEMS; k++) {
+            if (dig[k] != 0xffffffffu) {
+                const uint32_t slot = s_tilebin[dig[k]] + my_hist[dig[k]] + rank[k];
+                Item v; v.sp = sp[k]; v.cnt = cnt[k]; v.rest = rest[k]; v.idx = idx[k];
+                s_items[slot] = v;
+            }
+        }
+        __syncthreads();
+        const uint32_t tile_n = (uint32_t)(n - tile * ROUND_TILE < (uint64_t)ROUND_TILE ? n - tile * ROUND_TILE : (uint64_t)ROUND_TILE);
+        for (uint32_t j = threadIdx.x; j < tile_n; j += ROUND_THREADS) {
+            const Item v = s_items[j];
+            const uint64_t g = s_gbase[(uint32_t)((v.rest >> shift) & digit_mask)] + j;
+            if (io.items_out) io.items_out[g] = v;
+            if (io.sp_out) io.sp_out[g] = v.sp;
+            if (io.cnt_out) io.cnt_out[g] = v.cnt;
+            if (io.idx_out) io.idx_out[g] = v.idx;
+        }
+        __syncthreads();
+        }  // PART
     }
 }
 

@@ -67,7 +67,7 @@ struct svfm_session {
     cudaStream_t stream = nullptr;
     svfm::DeviceBuffer sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
-    svfm::DeviceBuffer pay0, pay1, rest0, rest1, val0, val1; // sweep search: items moving through the radix partitions
+    svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
     svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
     unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
@@ -379,8 +379,12 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
         p.m = ix->ext_m;
         p.prefix_bits = bits_for(ix->ext_entries) < 1 ? 1 : bits_for(ix->ext_entries);
         p.rest64 = (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits > 32;
-        const uint32_t t = 8u / p.bits;  // one radix pass (8-bit digit) per partition
-        p.steps_per_round = t < 1 ? 1 : (t > 3 ? 3 : t);
+        // steps per round: the partition digit (bits * steps) has at most ROUND_MAX_BINS values; more steps per round
+        // save partitions but interleave more symbol classes inside a round
+        static const uint32_t t_env = [] { const char* e = std::getenv("SVFM_SWEEP_STEPS"); return e ? (uint32_t)atoi(e) : 0u; }();
+        uint32_t t = t_env ? t_env : 8u / p.bits;
+        while (t > 1 && p.bits * t > 9) t--;
+        p.steps_per_round = t < 1 ? 1 : (t > 3 && !t_env ? 3 : t);
         return p;
     }
     if (n < sort_min_patterns()) return p;
@@ -483,8 +487,8 @@ static int run_build_ext(svfm_index* ix, int unused) {
     return SVFM_OK;
 }
 
-// Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps,
-// stable radix partition by the consumed symbols].  Leaves sp/cnt/idx of every item in work order.
+// Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps +
+// stable radix partition by the consumed symbols], each round ONE kernel.  Leaves sp/cnt/idx of every item in work order.
 template <class P, int NPL, int VBITS, class R>
 static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
                               void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {
@@ -494,82 +498,88 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     const uint32_t len = pb.fixed_len, m = plan.m, bits = plan.bits, T = plan.steps_per_round;
     const uint32_t remaining = len - m;
     const uint32_t rounds = remaining ? (remaining + T - 1) / T : 1;
+    const uint32_t digit_bits = bits * T, nb_max = 1u << digit_bits;
     using Pay = SweepPay<R>;
-    using Val = SweepVal<P>;
+    using Item = SweepItem<P, R>;
+    const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
     int rc;
     if ((rc = s->keys0.reserve(n * 4)) || (rc = s->keys1.reserve(n * 4)) || (rc = s->pay0.reserve(n * sizeof(Pay))) ||
-        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->vals0.reserve(n * 4)))
+        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->vals0.reserve(n * 4)) ||
+        (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + 64) * 4)) || (rc = s->sweep_desc.reserve(n_tiles * nb_max * 4)))
         return rc;
     const bool partitions = rounds > 1 || final_sort;
-    if (partitions && ((rc = s->rest0.reserve(n * sizeof(R))) || (rc = s->rest1.reserve(n * sizeof(R))) ||
-                       (rc = s->val0.reserve(n * sizeof(Val))) || (rc = s->val1.reserve(n * sizeof(Val)))))
-        return rc;
+    if (partitions && ((rc = s->items0.reserve(n * sizeof(Item))) || (rc = s->items1.reserve(n * sizeof(Item))))) return rc;
     cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
     cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
-    cub::DoubleBuffer<R> rest((R*)s->rest0.ptr, (R*)s->rest1.ptr);
-    cub::DoubleBuffer<Val> val((Val*)s->val0.ptr, (Val*)s->val1.ptr);
-    size_t t1 = 0, t2 = 0;
+    Item* items[2] = {(Item*)s->items0.ptr, (Item*)s->items1.ptr};
+    uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
+    uint32_t* tile_counters = hist + (uint64_t)rounds * nb_max;  // one per round
+    size_t t1 = 0;
     SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
-    if (partitions) SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, rest, val, (int64_t)n, 0, (int)(bits * T), s->stream));
-    if ((rc = s->cub_temp.reserve(t1 > t2 ? t1 : t2))) return rc;
+    if ((rc = s->cub_temp.reserve(t1))) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     {
         PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits + 7) / 8);
+        SVFM_CUDA(cudaMemsetAsync(hist, 0, ((uint64_t)rounds * nb_max + 64) * 4, s->stream));
         const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
         DevSyms syms;
         syms.symbol_count = ix->L.symbol_count;
         syms.s_eff = ix->symbols_present;
         std::memcpy(syms.sym_rank, ix->sym_rank, 64);
-        const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127);
+        const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) + (size_t)rounds * nb_max * 4;
         SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1, sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+        int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;
         if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
-        pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(), s->d_err);
+        pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(),
+                                                                            digit_bits, rounds, hist, s->d_err);
         SVFM_CUDA(cudaGetLastError());
         SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
     }
     uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
+    int cur = 0;  // items[cur] holds the current state from round 1 on
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t first = r * T;
         const uint32_t steps = remaining - first < T ? remaining - first : T;
         const bool last = r + 1 == rounds;
-        const bool sort_after = !last || final_sort;
-        SweepIO<P, R> io{};
+        const bool part = (!last || final_sort) && steps > 0;
+        // the last partition digit may be narrower than digit_bits: the histogram was taken on digit_bits bits, whose
+        // upper bits are then zero, so the wide digit sorts identically
+        const uint32_t nbins = nb_max;
+        SweepRoundIO<P, R> io{};
         if (r == 0) { io.prefix = prefix.Current(); io.pay = pay.Current(); }
-        else { io.rest_in = rest.Current(); io.val_in = val.Current(); }
-        if (sort_after) {
-            io.rest_out = r == 0 ? rest.Current() : nullptr;  // later rounds: rest is already in place
-            io.val_out = val.Current();
-        } else {
+        else io.items_in = items[cur];
+        if (last) {
             io.sp_out = (P*)d_sp_work;
             io.cnt_out = (P*)d_cnt_work;
             io.idx_out = idx_work;
+            io.heavy_seen = s->d_counters;
+        } else {
+            io.items_out = items[r == 0 ? 0 : cur ^ 1];
         }
-        if (last) io.heavy_seen = s->d_counters;
-        {
-            PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-            if (r == 0) {
-                const int grid = resident_grid(sweep_step_kernel<P, NPL, VBITS, R, true>, n, SEARCH_THREADS, ix->device);
-                sweep_step_kernel<P, NPL, VBITS, R, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, n, bits, bits * first, steps, io);
-            } else {
-                const int grid = resident_grid(sweep_step_kernel<P, NPL, VBITS, R, false>, n, SEARCH_THREADS, ix->device);
-                sweep_step_kernel<P, NPL, VBITS, R, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, n, bits, bits * first, steps, io);
-            }
+        io.hist = hist + (uint64_t)r * nb_max;
+        io.desc = (uint32_t*)s->sweep_desc.ptr;
+        io.tile_counter = tile_counters + r;
+        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+        if (part) SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
+        const size_t smem = part ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 : 0;
+        auto launch = [&](auto kernel) -> int {
+            if (smem > 48 * 1024) SVFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ROUND_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            uint64_t grid = n_tiles < (uint64_t)sms * per_sm ? n_tiles : (uint64_t)sms * per_sm;
+            kernel<<<(unsigned)grid, ROUND_THREADS, smem, s->stream>>>(dix, n, bits, bits * first, steps, nbins, io);
             SVFM_CUDA(cudaGetLastError());
-        }
-        if (sort_after && steps) {
-            PhaseTimer pt(s, SVFM_PHASE_PARTITION, 3);
-            SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t2, rest, val, (int64_t)n, (int)(bits * first),
-                                                      (int)(bits * (first + steps)), s->stream));
-        }
-        if (last && sort_after) {
-            PhaseTimer pt(s, SVFM_PHASE_PARTITION, 1);
-            sweep_unzip_kernel<P><<<grid_for(n, SEARCH_THREADS, ix->device), SEARCH_THREADS, 0, s->stream>>>(
-                val.Current(), n, (P*)d_sp_work, (P*)d_cnt_work, idx_work);
-            SVFM_CUDA(cudaGetLastError());
-        }
+            return SVFM_OK;
+        };
+        if (r == 0 && part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, true>);
+        else if (r == 0) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, false>);
+        else if (part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, true>);
+        else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, false>);
+        if (rc) return rc;
+        if (r > 0 && !last) cur ^= 1;
     }
     *idx_out = idx_work;
     return SVFM_OK;
@@ -735,6 +745,12 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
         case 128: SVFM_DISPATCH_N(P, 128, FN, __VA_ARGS__)                  \
         default: return SVFM_ERR_BAD_TYPE;                                  \
     }
+#ifdef SVFM_ONLY_CFG1  /* developer builds: only FmIndex<u32, Block3<u64>> (seconds instead of minutes to compile) */
+#undef SVFM_DISPATCH_V
+#define SVFM_DISPATCH_V(P, FN, ...) \
+    if (t.vec_bits == 64 && t.planes == 3) return FN<P, 3, 64>(__VA_ARGS__); \
+    return SVFM_ERR_BAD_TYPE;
+#endif
 #define SVFM_DISPATCH(FN, ...)                                              \
     do {                                                                    \
         const svfm_type& t = s->ix->type;                                   \
