@@ -135,6 +135,26 @@ def build_index_on_device(L, torch, fm, n, seed, device):
     return d_text, d_blob, size, it, enc, {"synth_text_s": round(t1 - t0, 3), "build_s": round(t2 - t1, 3)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process (and the library's worker threads, which inherit the mask) to the CPUs NVML reports as local
+    to the GPU, so that the pinned host buffers of the end-to-end path are allocated on the GPU's NUMA node and several
+    ranks do not share one socket's memory controllers.  Best effort; returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def roofline_traffic(kernel: str, batch: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this same workload (profiles/roofline_traffic.json), or None."""
@@ -162,6 +182,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     L = _ffi.lib()
@@ -352,6 +374,7 @@ def run_ours(args):
     # ---- CPU baseline: the oracle (reference algorithm) on the host cores, bounded sample, rank 0 at N=1 -------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
         from oracle import pyoracle as po
         ora = po.OracleFmIndex.load(host_blob, po.IndexType(32, 3, 64, True))
         cores = os.cpu_count() or 1
@@ -435,7 +458,7 @@ def run_ours(args):
                        "text_len": n, "patterns_per_gpu_per_step": B, "pattern_len": plen, "blob_bytes": int(info.blob_len),
                        "sharding": f"index replicated, patterns sharded over {world} GPU(s), no collective",
                        "l2_policy": "inputs larger than L2 (2 GB of patterns + 2.7 GB index per step), no flush",
-                       "distinct_batches": n_distinct},
+                       "distinct_batches": n_distinct, "cpus_bound_to_gpu_numa_node": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "gather_roofline": gather, "count_only_patterns_per_s": count_only,
