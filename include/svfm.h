@@ -167,7 +167,7 @@ void svfm_host_free(void* p);
  *                      locality-sorted by their trailing symbols before the search kernel (0 = always,
  *                      UINT64_MAX = never; default 131072; env SVFM_SORT_MIN).
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
- *                      pipeline upload / kernels / download (0 = one chunk; default 16 Mi; env SVFM_CHUNK).
+ *                      pipeline upload / kernels / download (0 = one chunk; default 8 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
  *                      kept sorted by SA position and moves through the index as streams (default 1 Mi; env
  *                      SVFM_SWEEP_MIN).

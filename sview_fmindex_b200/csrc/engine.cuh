@@ -1,0 +1,454 @@
+// engine.cuh -- internals shared by the translation units of libsvfm.so: the index / session handles, the per-type
+// kernel launchers (templates over <Position, planes, Vector bits>) and the table through which svfm_api.cu reaches
+// them.  The 30 (P, BlockN, Vector) instantiations are spread over inst_p*_v*.cu so that they compile in parallel.
+// Citations are relative to the reference's sview-fmindex/src/.
+#pragma once
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "blob_layout.h"
+#include "common.cuh"
+#include "search_kernels.cuh"
+
+struct svfm_uploader;
+
+struct svfm_index {
+    svfm_type type;
+    svfm::Layout L;
+    int device = 0;
+    uint8_t* d_alloc = nullptr;  // cudaMalloc base
+    uint8_t* d_blob = nullptr;   // d_alloc + pad: the blob, byte-for-byte
+    uint64_t blob_len = 0;
+    uint64_t text_len = 0;
+    uint64_t sentinel_index = 0;
+    uint32_t symbols_present = 0;  // symbols with at least one occurrence in the text (from count_array)
+    uint8_t sym_rank[64];          // symbol index -> rank among the occurring symbols (0xff: never occurs)
+    uint8_t present[64];           // rank -> symbol index
+    uint32_t ext_m = 0;            // extended k-mer table: symbols resolved per lookup (0 = no table)
+    uint64_t ext_entries = 0;
+    void* d_ext = nullptr;         // P[2 * ext_entries]
+    std::mutex pool_mu;
+    std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
+    std::vector<svfm_uploader*> up_pool;  // idle uploaders
+};
+
+// Upload side of the host-buffer entry points: ONE stream keeps the host->device copy engine busy with the chunks
+// of a batch back to back, into one device buffer; the worker sessions wait on a per-chunk event.
+struct svfm_uploader {
+    cudaStream_t stream = nullptr;
+    svfm::DeviceBuffer pats, offs;
+    std::vector<cudaEvent_t> ev;
+};
+
+struct svfm_session {
+    svfm_index* ix = nullptr;
+    cudaStream_t stream = nullptr;
+    svfm::DeviceBuffer sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
+    svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
+    svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
+    svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
+    unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
+    int* d_err = nullptr;
+    uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
+    // per-phase timing (svfm_session_set_timing)
+    bool timing = false;
+    struct Span { int phase; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> free_events;
+    double phase_ms[SVFM_PHASE_MAX] = {0};
+    uint64_t phase_launches[SVFM_PHASE_MAX] = {0};
+};
+
+namespace svfm {
+
+template <class P>
+static DevIndex<P> make_dev_index(const svfm_index* ix) {
+    const Layout& L = ix->L;
+    DevIndex<P> d;
+    d.count_array = reinterpret_cast<const P*>(ix->d_blob + L.off_count_array);
+    d.kmer_multiplier = reinterpret_cast<const uint64_t*>(ix->d_blob + L.off_kmer_multiplier);
+    d.kmer_count_table = reinterpret_cast<const P*>(ix->d_blob + L.off_kmer_count_table);
+    d.suffix_array = reinterpret_cast<const P*>(ix->d_blob + L.off_suffix_array);
+    d.rank_checkpoints = reinterpret_cast<const P*>(ix->d_blob + L.off_rank_checkpoints);
+    d.blocks = ix->d_blob + L.off_blocks;
+    d.table = ix->type.encoder ? ix->d_blob + L.off_encoder : nullptr;
+    d.sentinel_index = (P)ix->sentinel_index;
+    d.symbol_count = L.bwm_symbol_count;
+    d.kmer_size = L.kmer_size;
+    d.sampling_ratio = L.sampling_ratio;
+    const uint32_t r = L.sampling_ratio;
+    if ((r & (r - 1)) == 0) {
+        d.ratio_mask = r - 1;
+        d.ratio_shift = 0;
+        while ((1u << d.ratio_shift) < r) d.ratio_shift++;
+    } else {
+        d.ratio_mask = 0xffffffffu;
+        d.ratio_shift = 0;
+    }
+    d.ext = reinterpret_cast<const P*>(ix->d_ext);
+    d.ext_m = ix->ext_m;
+    d.s_eff = ix->symbols_present;
+    std::memcpy(d.sym_rank, ix->sym_rank, 64);
+    std::memcpy(d.present, ix->present, 64);
+    return d;
+}
+
+
+// RAII span: records CUDA events around the kernels of one phase when timing is on.
+struct PhaseTimer {
+    svfm_session* s;
+    int phase;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    PhaseTimer(svfm_session* s_, int phase_, uint64_t launches) : s(s_), phase(phase_) {
+        s->phase_launches[phase] += launches;
+        g_launches += launches;
+        if (!s->timing) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!s->free_events.empty()) { e = s->free_events.back(); s->free_events.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, s->stream);
+    }
+    ~PhaseTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, s->stream);
+        s->spans.push_back({phase, e0, e1});
+    }
+};
+
+// Grid for a grid-stride kernel: a multiple of the CTAs that can be resident at once (SMs x occupancy);
+// fewer when the work does not fill the machine.  Measured on B200 (1 Gbp index, 100M patterns): 4 resident
+// waves run the search kernel 13% faster than exactly one (shorter per-thread item chains, less tail).
+template <class K>
+static int resident_grid(K kernel, uint64_t work_items, int threads, int device) {
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    static const double mult = [] { const char* e = std::getenv("SVFM_GRID_MULT"); return e ? atof(e) : 4.0; }();
+    const uint64_t cap = (uint64_t)((double)sms * per_sm * mult);
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+static int grid_for(uint64_t work_items, int threads, int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sms * 8;  // a whole number of waves of resident CTAs; grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+
+// Batch plans.  Everything that has to change order moves through radix sorts (streaming passes), never through
+// random scatters: on B200 one random 32 B sector access costs as much HBM time as streaming ~120 bytes.
+//   sweep  : dense fixed-length batch -> items sorted by SA interval, rounds of backward steps + radix partition
+//            (search_kernels.cuh, "sweep search")
+//   sorted : locality sort by trailing symbols, one search kernel (variable-length or long patterns)
+//   neither: search kernel in the caller's order (small batches)
+struct SortPlan {
+    bool sorted = false;
+    uint32_t bits = 0;     // bits per symbol in the packed key
+    int begin_bit = 0, end_bit = 64;
+    bool sweep = false;
+    uint32_t m = 0;            // sweep: trailing symbols resolved by the extended table
+    int prefix_bits = 0;       // sweep: significant bits of the table index
+    uint32_t steps_per_round = 1;
+    bool rest64 = false;       // sweep: the other symbols need a 64-bit word
+};
+
+
+static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
+    int b = 0;
+    while (b < 63 && (1ull << b) < n) b++;
+    return b;
+}
+
+
+// One launch of the search kernel: keys/idx (or NULL) in, sp/cnt out.
+template <class P, int NPL, int VBITS>
+static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
+                      void* d_sp_work, void* d_cnt_work) {
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+    SearchIO<P> io{};
+    io.keys = keys;
+    io.idx = idx;
+    io.bits = bits;
+    io.sp_out = (P*)d_sp_work;
+    io.cnt_out = (P*)d_cnt_work;
+    io.heavy_seen = s->d_counters;
+    io.err = s->d_err;
+    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+    SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+
+// Extended k-mer table, built once per index right after the upload (search_kernels.cuh).
+template <class P, int NPL, int VBITS>
+static int run_build_ext(svfm_index* ix, uint64_t ext_bits) {
+    const uint64_t s_eff = ix->symbols_present;
+    uint64_t budget = 1ull << (ext_bits > 32 ? 32 : ext_bits);
+    if (ext_bits == 0 || s_eff < 2 || s_eff > 64) return SVFM_OK;
+    const uint64_t by_text = ix->text_len / 2 > s_eff ? ix->text_len / 2 : s_eff;
+    if (budget > by_text) budget = by_text;
+    uint32_t m = 1;
+    uint64_t entries = s_eff;
+    while (entries * s_eff <= budget && m < 31) { entries *= s_eff; m++; }
+    if (entries > 0xfffffff0ull) return SVFM_OK;
+    DevIndex<P> dix = make_dev_index<P>(ix);
+    P *a = nullptr, *b = nullptr;
+    SVFM_CUDA(cudaMalloc(&a, entries * 2 * sizeof(P)));
+    if (m > 1) {
+        cudaError_t e = cudaMalloc(&b, entries / s_eff * 2 * sizeof(P));
+        if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
+    }
+    // levels alternate between the two buffers so that level m lands in `a`
+    P* cur = (m % 2 == 1) ? a : b;
+    P* other = (m % 2 == 1) ? b : a;
+    ext_level1_kernel<P><<<1, 64>>>(dix, cur);
+    g_launches++;
+    uint64_t n_in = s_eff;
+    for (uint32_t j = 1; j < m; j++) {
+        const int grid = resident_grid(ext_expand_kernel<P, NPL, VBITS>, n_in * s_eff, SEARCH_THREADS, ix->device);
+        ext_expand_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS>>>(dix, cur, n_in, other);
+        g_launches++;
+        std::swap(cur, other);
+        n_in *= s_eff;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (b) cudaFree(b);
+    if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
+    ix->d_ext = a;
+    ix->ext_m = m;
+    ix->ext_entries = entries;
+    return SVFM_OK;
+}
+
+// Output of the type-independent front of the sweep search (svfm_api.cu): items packed and radix-sorted by table index,
+// digit histograms of every round followed by one zeroed tile counter per round.
+struct SweepPre {
+    const uint32_t* prefix;
+    const void* pay;   // SweepPay<R>[n]
+    uint32_t* hist;    // [rounds][1 << (bits * steps_per_round)] then [rounds] tile counters
+};
+template <class R>
+int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, uint32_t rounds, SweepPre* out);
+extern template int run_sweep_presort<uint32_t>(svfm_session*, const PatternBatch&, const SortPlan&, uint32_t, SweepPre*);
+extern template int run_sweep_presort<uint64_t>(svfm_session*, const PatternBatch&, const SortPlan&, uint32_t, SweepPre*);
+
+// Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps +
+// stable radix partition by the consumed symbols], each round ONE kernel.  Leaves sp/cnt/idx of every item in work order.
+template <class P, int NPL, int VBITS, class R>
+static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
+                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {
+    const svfm_index* ix = s->ix;
+    const DevIndex<P> dix = make_dev_index<P>(ix);
+    const uint64_t n = pb.n;
+    const uint32_t len = pb.fixed_len, m = plan.m, bits = plan.bits, T = plan.steps_per_round;
+    const uint32_t remaining = len - m;
+    const uint32_t rounds = remaining ? (remaining + T - 1) / T : 1;
+    const uint32_t digit_bits = bits * T, nb_max = 1u << digit_bits;
+    using Pay = SweepPay<R>;
+    using Item = SweepItem<P, R>;
+    const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
+    int rc;
+    if ((rc = s->vals0.reserve(n * 4)) || (rc = s->sweep_desc.reserve(n_tiles * nb_max * 4))) return rc;
+    const bool partitions = rounds > 1 || final_sort;
+    if (partitions && ((rc = s->items0.reserve(n * sizeof(Item))) || (rc = s->items1.reserve(n * sizeof(Item))))) return rc;
+    Item* items[2] = {(Item*)s->items0.ptr, (Item*)s->items1.ptr};
+    SweepPre pre{};
+    if ((rc = run_sweep_presort<R>(s, pb, plan, rounds, &pre))) return rc;  // pack + radix sort by table index (svfm_api.cu)
+    const uint32_t* prefix = pre.prefix;
+    const Pay* pay = (const Pay*)pre.pay;
+    uint32_t* hist = pre.hist;
+    uint32_t* tile_counters = hist + (uint64_t)rounds * nb_max;  // one per round
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
+    int cur = 0;  // items[cur] holds the current state from round 1 on
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t first = r * T;
+        const uint32_t steps = remaining - first < T ? remaining - first : T;
+        const bool last = r + 1 == rounds;
+        const bool part = (!last || final_sort) && steps > 0;
+        // the last partition digit may be narrower than digit_bits: the histogram was taken on digit_bits bits, whose
+        // upper bits are then zero, so the wide digit sorts identically
+        const uint32_t nbins = nb_max;
+        SweepRoundIO<P, R> io{};
+        if (r == 0) { io.prefix = prefix; io.pay = pay; }
+        else io.items_in = items[cur];
+        if (last) {
+            io.sp_out = (P*)d_sp_work;
+            io.cnt_out = (P*)d_cnt_work;
+            io.idx_out = idx_work;
+            io.heavy_seen = s->d_counters;
+        } else {
+            io.items_out = items[r == 0 ? 0 : cur ^ 1];
+        }
+        io.hist = hist + (uint64_t)r * nb_max;
+        io.desc = (uint32_t*)s->sweep_desc.ptr;
+        io.tile_counter = tile_counters + r;
+        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+        if (part) SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
+        const size_t smem = part ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 : 0;
+        auto launch = [&](auto kernel) -> int {
+            if (smem > 48 * 1024) SVFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ROUND_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            uint64_t grid = n_tiles < (uint64_t)sms * per_sm ? n_tiles : (uint64_t)sms * per_sm;
+            kernel<<<(unsigned)grid, ROUND_THREADS, smem, s->stream>>>(dix, n, bits, bits * first, steps, nbins, io);
+            SVFM_CUDA(cudaGetLastError());
+            return SVFM_OK;
+        };
+        if (r == 0 && part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, true>);
+        else if (r == 0) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, false>);
+        else if (part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, true>);
+        else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, false>);
+        if (rc) return rc;
+        if (r > 0 && !last) cur ^= 1;
+    }
+    *idx_out = idx_work;
+    return SVFM_OK;
+}
+
+template <class P, int NPL, int VBITS>
+static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
+                            void* d_cnt_work, const uint32_t** idx_out) {
+    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
+    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
+}
+
+template <class P>
+struct WidenCounts {
+    const P* cnt;
+    uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)cnt[i] : 0ull; }
+};
+
+template <class P>
+static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) {
+    // out_offs[0..n] = exclusive prefix sums of the counts, widened to u64 (out_offs[n] = total)
+    WidenCounts<P> f{(const P*)d_cnt, n};
+    auto in = thrust::make_transform_iterator(thrust::counting_iterator<uint64_t>(0), f);
+    size_t temp = 0;
+    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_out_offs, n + 1, s->stream));
+    int rc = s->cub_temp.reserve(temp);
+    if (rc) return rc;
+    PhaseTimer pt(s, SVFM_PHASE_SCAN, 2);
+    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_temp.ptr, temp, in, d_out_offs, n + 1, s->stream));
+    return SVFM_OK;
+}
+
+
+// LF-walk + sampled-SA lookup for every SA row of every pattern (SVFM_PHASE_LOCATE).
+template <class P, int NPL, int VBITS>
+static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
+                      const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
+    if (total == 0) return SVFM_OK;
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    HeavyList<P> heavy{nullptr, nullptr, nullptr, nullptr, s->d_counters + 1, 0};
+    int rc;
+    if (heavy_seen) {
+        if ((rc = s->heavy_sp.reserve(heavy_seen * sizeof(P))) || (rc = s->heavy_cnt.reserve((heavy_seen + 1) * sizeof(P))) ||
+            (rc = s->heavy_obase.reserve(heavy_seen * sizeof(uint64_t))) || (rc = s->heavy_pat.reserve(heavy_seen * 4)) ||
+            (rc = s->heavy_offs.reserve((heavy_seen + 1) * sizeof(uint64_t))))
+            return rc;
+        heavy.sp = (P*)s->heavy_sp.ptr;
+        heavy.cnt = (P*)s->heavy_cnt.ptr;
+        heavy.obase = (uint64_t*)s->heavy_obase.ptr;
+        heavy.pat = (uint32_t*)s->heavy_pat.ptr;
+        heavy.capacity = heavy_seen;
+    }
+    {
+        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS>, n, LOCATE_THREADS, s->ix->device);
+        locate_warp_kernel<P, NPL, VBITS><<<grid, LOCATE_THREADS, 0, s->stream>>>(
+            dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+        SVFM_CUDA(cudaGetLastError());
+    }
+    if (!heavy_seen) return SVFM_OK;
+    // patterns with more than HEAVY_ROWS rows: one thread per row
+    if ((rc = run_scan<P>(s, heavy_seen, heavy.cnt, (uint64_t*)s->heavy_offs.ptr))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[2], (uint64_t*)s->heavy_offs.ptr + heavy_seen, sizeof(uint64_t),
+                              cudaMemcpyDeviceToHost, s->stream));
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    const uint64_t heavy_total = s->h_pinned[2];
+    const uint64_t blocks = (heavy_total + LOCATE_THREADS - 1) / LOCATE_THREADS;
+    if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
+    if (blocks) {
+        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        locate_rows_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
+            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
+            (P*)d_positions, d_rec_key);
+        SVFM_CUDA(cudaGetLastError());
+    }
+    return SVFM_OK;
+}
+
+
+// ---- per-(Position, Vector) entry points; `planes` picks Block2..Block6 ------------------------------------------
+struct TypeOps {
+    int (*search)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
+                  void* d_sp_work, void* d_cnt_work);
+    int (*build_ext)(uint32_t planes, svfm_index* ix, uint64_t ext_bits);
+    int (*search_sweep)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
+                        void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out);
+    int (*locate)(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
+                  const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key);
+};
+
+#define SVFM_PLANES_SWITCH(P, VB, FN, ...)          \
+    switch (planes) {                               \
+        case 2: return FN<P, 2, VB>(__VA_ARGS__);   \
+        case 3: return FN<P, 3, VB>(__VA_ARGS__);   \
+        case 4: return FN<P, 4, VB>(__VA_ARGS__);   \
+        case 5: return FN<P, 5, VB>(__VA_ARGS__);   \
+        case 6: return FN<P, 6, VB>(__VA_ARGS__);   \
+        default: return SVFM_ERR_BAD_TYPE;          \
+    }
+
+// One translation unit per (P, VB): defines `const TypeOps NAME`.
+#define SVFM_DEFINE_TYPE_OPS(NAME, P, VB)                                                                                          \
+    static int NAME##_search(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx,   \
+                             uint32_t bits, void* d_sp_work, void* d_cnt_work) {                                                    \
+        SVFM_PLANES_SWITCH(P, VB, run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work)                                        \
+    }                                                                                                                               \
+    static int NAME##_build_ext(uint32_t planes, svfm_index* ix, uint64_t ext_bits) {                                               \
+        SVFM_PLANES_SWITCH(P, VB, run_build_ext, ix, ext_bits)                                                                      \
+    }                                                                                                                               \
+    static int NAME##_search_sweep(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, \
+                                   void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {                                   \
+        SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out)                        \
+    }                                                                                                                               \
+    static int NAME##_locate(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work,              \
+                             const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen,                   \
+                             void* d_positions, uint32_t* d_rec_key) {                                                              \
+        SVFM_PLANES_SWITCH(P, VB, run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key)  \
+    }                                                                                                                               \
+    extern const TypeOps NAME;                                                                                                      \
+    const TypeOps NAME = {NAME##_search, NAME##_build_ext, NAME##_search_sweep, NAME##_locate};
+
+extern const TypeOps ops_p32_v32, ops_p32_v64, ops_p32_v128, ops_p64_v32, ops_p64_v64, ops_p64_v128;
+
+}  // namespace svfm

@@ -58,7 +58,7 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, const P* __
 // a suffix walk the same checkpoint rows and blocks for as many steps as the shared suffix is long).
 // The key doubles as the encoded pattern: the search kernel takes the last min(len, 64/bits) symbols from
 // it and never touches the pattern bytes again unless the pattern is longer.  Also validates the batch.
-__global__ void __launch_bounds__(SEARCH_THREADS)
+static __global__ void __launch_bounds__(SEARCH_THREADS)
 pack_keys_kernel(const uint8_t* __restrict__ table, uint32_t S, const PatternBatch pb, uint32_t bits,
                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ err) {
     __shared__ uint8_t s_table[256];
@@ -764,7 +764,7 @@ locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_
 // CSR offsets from the pattern indices of the records once they are sorted by pattern: first[k] = index of
 // the first record of pattern k (patterns without records keep the 0xff.. fill); out_offs is then the
 // reverse running minimum of `first` with out_offs[n] = total (done with a device scan by the caller).
-__global__ void run_starts_kernel(const uint32_t* __restrict__ sorted_key, uint64_t total, uint64_t* __restrict__ first) {
+static __global__ void run_starts_kernel(const uint32_t* __restrict__ sorted_key, uint64_t total, uint64_t* __restrict__ first) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t k = sorted_key[t];
         if (t == 0 || sorted_key[t - 1] != k) first[k] = t;

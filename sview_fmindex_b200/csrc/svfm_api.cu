@@ -18,9 +18,9 @@
 #include <thrust/iterator/reverse_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
-#include "blob_layout.h"
-#include "common.cuh"
-#include "search_kernels.cuh"
+#include <thrust/iterator/reverse_iterator.h>
+
+#include "engine.cuh"
 
 namespace svfm {
 
@@ -32,89 +32,7 @@ std::atomic<uint64_t> g_launches{0};
 // ---------------------------------------------------------------------------------------------
 }  // namespace svfm
 
-struct svfm_uploader;
-
-struct svfm_index {
-    svfm_type type;
-    svfm::Layout L;
-    int device = 0;
-    uint8_t* d_alloc = nullptr;  // cudaMalloc base
-    uint8_t* d_blob = nullptr;   // d_alloc + pad: the blob, byte-for-byte
-    uint64_t blob_len = 0;
-    uint64_t text_len = 0;
-    uint64_t sentinel_index = 0;
-    uint32_t symbols_present = 0;  // symbols with at least one occurrence in the text (from count_array)
-    uint8_t sym_rank[64];          // symbol index -> rank among the occurring symbols (0xff: never occurs)
-    uint8_t present[64];           // rank -> symbol index
-    uint32_t ext_m = 0;            // extended k-mer table: symbols resolved per lookup (0 = no table)
-    uint64_t ext_entries = 0;
-    void* d_ext = nullptr;         // P[2 * ext_entries]
-    std::mutex pool_mu;
-    std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
-    std::vector<svfm_uploader*> up_pool;  // idle uploaders
-};
-
-// Upload side of the host-buffer entry points: ONE stream keeps the host->device copy engine busy with the chunks
-// of a batch back to back, into one device buffer; the worker sessions wait on a per-chunk event.
-struct svfm_uploader {
-    cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer pats, offs;
-    std::vector<cudaEvent_t> ev;
-};
-
-struct svfm_session {
-    svfm_index* ix = nullptr;
-    cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
-    svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
-    svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
-    svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
-    svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
-    unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
-    int* d_err = nullptr;
-    uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
-    // per-phase timing (svfm_session_set_timing)
-    bool timing = false;
-    struct Span { int phase; cudaEvent_t e0, e1; };
-    std::vector<Span> spans;
-    std::vector<cudaEvent_t> free_events;
-    double phase_ms[SVFM_PHASE_MAX] = {0};
-    uint64_t phase_launches[SVFM_PHASE_MAX] = {0};
-};
-
 namespace svfm {
-
-template <class P>
-static DevIndex<P> make_dev_index(const svfm_index* ix) {
-    const Layout& L = ix->L;
-    DevIndex<P> d;
-    d.count_array = reinterpret_cast<const P*>(ix->d_blob + L.off_count_array);
-    d.kmer_multiplier = reinterpret_cast<const uint64_t*>(ix->d_blob + L.off_kmer_multiplier);
-    d.kmer_count_table = reinterpret_cast<const P*>(ix->d_blob + L.off_kmer_count_table);
-    d.suffix_array = reinterpret_cast<const P*>(ix->d_blob + L.off_suffix_array);
-    d.rank_checkpoints = reinterpret_cast<const P*>(ix->d_blob + L.off_rank_checkpoints);
-    d.blocks = ix->d_blob + L.off_blocks;
-    d.table = ix->type.encoder ? ix->d_blob + L.off_encoder : nullptr;
-    d.sentinel_index = (P)ix->sentinel_index;
-    d.symbol_count = L.bwm_symbol_count;
-    d.kmer_size = L.kmer_size;
-    d.sampling_ratio = L.sampling_ratio;
-    const uint32_t r = L.sampling_ratio;
-    if ((r & (r - 1)) == 0) {
-        d.ratio_mask = r - 1;
-        d.ratio_shift = 0;
-        while ((1u << d.ratio_shift) < r) d.ratio_shift++;
-    } else {
-        d.ratio_mask = 0xffffffffu;
-        d.ratio_shift = 0;
-    }
-    d.ext = reinterpret_cast<const P*>(ix->d_ext);
-    d.ext_m = ix->ext_m;
-    d.s_eff = ix->symbols_present;
-    std::memcpy(d.sym_rank, ix->sym_rank, 64);
-    std::memcpy(d.present, ix->present, 64);
-    return d;
-}
 
 static int finish_load(svfm_index* ix) {
     // text length is not stored in a header: it equals count_array[S] (count_array.rs:117,125)
@@ -244,32 +162,6 @@ static void session_delete(svfm_session* s) {
     delete s;
 }
 
-// RAII span: records CUDA events around the kernels of one phase when timing is on.
-struct PhaseTimer {
-    svfm_session* s;
-    int phase;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    PhaseTimer(svfm_session* s_, int phase_, uint64_t launches) : s(s_), phase(phase_) {
-        s->phase_launches[phase] += launches;
-        g_launches += launches;
-        if (!s->timing) return;
-        auto get = [&]() {
-            cudaEvent_t e;
-            if (!s->free_events.empty()) { e = s->free_events.back(); s->free_events.pop_back(); }
-            else cudaEventCreate(&e);
-            return e;
-        };
-        e0 = get();
-        e1 = get();
-        cudaEventRecord(e0, s->stream);
-    }
-    ~PhaseTimer() {
-        if (!e0) return;
-        cudaEventRecord(e1, s->stream);
-        s->spans.push_back({phase, e0, e1});
-    }
-};
-
 static void collect_spans(svfm_session* s) {
     for (auto& sp : s->spans) {
         float ms = 0;
@@ -297,52 +189,6 @@ struct SessionLease {
     }
 };
 
-// ---------------------------------------------------------------------------------------------
-// kernel dispatch over the 30 (P, BlockN, Vector) instantiations
-// ---------------------------------------------------------------------------------------------
-// Grid for a grid-stride kernel: a multiple of the CTAs that can be resident at once (SMs x occupancy);
-// fewer when the work does not fill the machine.  Measured on B200 (1 Gbp index, 100M patterns): 4 resident
-// waves run the search kernel 13% faster than exactly one (shorter per-thread item chains, less tail).
-template <class K>
-static int resident_grid(K kernel, uint64_t work_items, int threads, int device) {
-    int sms = 148, per_sm = 1;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    uint64_t blocks = (work_items + threads - 1) / threads;
-    static const double mult = [] { const char* e = std::getenv("SVFM_GRID_MULT"); return e ? atof(e) : 4.0; }();
-    const uint64_t cap = (uint64_t)((double)sms * per_sm * mult);
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) blocks = 1;
-    return (int)blocks;
-}
-
-static int grid_for(uint64_t work_items, int threads, int device) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    uint64_t blocks = (work_items + threads - 1) / threads;
-    const uint64_t cap = (uint64_t)sms * 8;  // a whole number of waves of resident CTAs; grid-stride beyond
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) blocks = 1;
-    return (int)blocks;
-}
-
-// Batch plans.  Everything that has to change order moves through radix sorts (streaming passes), never through
-// random scatters: on B200 one random 32 B sector access costs as much HBM time as streaming ~120 bytes.
-//   sweep  : dense fixed-length batch -> items sorted by SA interval, rounds of backward steps + radix partition
-//            (search_kernels.cuh, "sweep search")
-//   sorted : locality sort by trailing symbols, one search kernel (variable-length or long patterns)
-//   neither: search kernel in the caller's order (small batches)
-struct SortPlan {
-    bool sorted = false;
-    uint32_t bits = 0;     // bits per symbol in the packed key
-    int begin_bit = 0, end_bit = 64;
-    bool sweep = false;
-    uint32_t m = 0;            // sweep: trailing symbols resolved by the extended table
-    int prefix_bits = 0;       // sweep: significant bits of the table index
-    uint32_t steps_per_round = 1;
-    bool rest64 = false;       // sweep: the other symbols need a 64-bit word
-};
-
 static std::atomic<uint64_t> g_sort_min{[] {
     const char* e = std::getenv("SVFM_SORT_MIN");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 17);
@@ -360,12 +206,6 @@ static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once 
     const char* e = std::getenv("SVFM_SWEEP_FINAL_SORT");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
-
-static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
-    int b = 0;
-    while (b < 63 && (1ull << b) < n) b++;
-    return b;
-}
 
 static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& pb) {
     SortPlan p;
@@ -425,197 +265,9 @@ static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& 
     return SVFM_OK;
 }
 
-// One launch of the search kernel: keys/idx (or NULL) in, sp/cnt out.
-template <class P, int NPL, int VBITS>
-static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                      void* d_sp_work, void* d_cnt_work) {
-    const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
-    SearchIO<P> io{};
-    io.keys = keys;
-    io.idx = idx;
-    io.bits = bits;
-    io.sp_out = (P*)d_sp_work;
-    io.cnt_out = (P*)d_cnt_work;
-    io.heavy_seen = s->d_counters;
-    io.err = s->d_err;
-    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
-    SVFM_CUDA(cudaGetLastError());
-    return SVFM_OK;
-}
-
-// Extended k-mer table, built once per index right after the upload (search_kernels.cuh).
-template <class P, int NPL, int VBITS>
-static int run_build_ext(svfm_index* ix, int unused) {
-    (void)unused;
-    const uint64_t s_eff = ix->symbols_present;
-    uint64_t budget = 1ull << (g_ext_bits.load() > 32 ? 32 : g_ext_bits.load());
-    if (g_ext_bits.load() == 0 || s_eff < 2 || s_eff > 64) return SVFM_OK;
-    const uint64_t by_text = ix->text_len / 2 > s_eff ? ix->text_len / 2 : s_eff;
-    if (budget > by_text) budget = by_text;
-    uint32_t m = 1;
-    uint64_t entries = s_eff;
-    while (entries * s_eff <= budget && m < 31) { entries *= s_eff; m++; }
-    if (entries > 0xfffffff0ull) return SVFM_OK;
-    DevIndex<P> dix = make_dev_index<P>(ix);
-    P *a = nullptr, *b = nullptr;
-    SVFM_CUDA(cudaMalloc(&a, entries * 2 * sizeof(P)));
-    if (m > 1) {
-        cudaError_t e = cudaMalloc(&b, entries / s_eff * 2 * sizeof(P));
-        if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
-    }
-    // levels alternate between the two buffers so that level m lands in `a`
-    P* cur = (m % 2 == 1) ? a : b;
-    P* other = (m % 2 == 1) ? b : a;
-    ext_level1_kernel<P><<<1, 64>>>(dix, cur);
-    g_launches++;
-    uint64_t n_in = s_eff;
-    for (uint32_t j = 1; j < m; j++) {
-        const int grid = resident_grid(ext_expand_kernel<P, NPL, VBITS>, n_in * s_eff, SEARCH_THREADS, ix->device);
-        ext_expand_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS>>>(dix, cur, n_in, other);
-        g_launches++;
-        std::swap(cur, other);
-        n_in *= s_eff;
-    }
-    cudaError_t e = cudaDeviceSynchronize();
-    if (b) cudaFree(b);
-    if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
-    ix->d_ext = a;
-    ix->ext_m = m;
-    ix->ext_entries = entries;
-    return SVFM_OK;
-}
-
-// Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps +
-// stable radix partition by the consumed symbols], each round ONE kernel.  Leaves sp/cnt/idx of every item in work order.
-template <class P, int NPL, int VBITS, class R>
-static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
-                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {
-    const svfm_index* ix = s->ix;
-    const DevIndex<P> dix = make_dev_index<P>(ix);
-    const uint64_t n = pb.n;
-    const uint32_t len = pb.fixed_len, m = plan.m, bits = plan.bits, T = plan.steps_per_round;
-    const uint32_t remaining = len - m;
-    const uint32_t rounds = remaining ? (remaining + T - 1) / T : 1;
-    const uint32_t digit_bits = bits * T, nb_max = 1u << digit_bits;
-    using Pay = SweepPay<R>;
-    using Item = SweepItem<P, R>;
-    const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
-    int rc;
-    if ((rc = s->keys0.reserve(n * 4)) || (rc = s->keys1.reserve(n * 4)) || (rc = s->pay0.reserve(n * sizeof(Pay))) ||
-        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->vals0.reserve(n * 4)) ||
-        (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + 64) * 4)) || (rc = s->sweep_desc.reserve(n_tiles * nb_max * 4)))
-        return rc;
-    const bool partitions = rounds > 1 || final_sort;
-    if (partitions && ((rc = s->items0.reserve(n * sizeof(Item))) || (rc = s->items1.reserve(n * sizeof(Item))))) return rc;
-    cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
-    cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
-    Item* items[2] = {(Item*)s->items0.ptr, (Item*)s->items1.ptr};
-    uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
-    uint32_t* tile_counters = hist + (uint64_t)rounds * nb_max;  // one per round
-    size_t t1 = 0;
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
-    if ((rc = s->cub_temp.reserve(t1))) return rc;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-    {
-        PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits + 7) / 8);
-        SVFM_CUDA(cudaMemsetAsync(hist, 0, ((uint64_t)rounds * nb_max + 64) * 4, s->stream));
-        const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
-        DevSyms syms;
-        syms.symbol_count = ix->L.symbol_count;
-        syms.s_eff = ix->symbols_present;
-        std::memcpy(syms.sym_rank, ix->sym_rank, 64);
-        const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) + (size_t)rounds * nb_max * 4;
-        SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;
-        if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
-        pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, m, prefix.Current(), pay.Current(),
-                                                                            digit_bits, rounds, hist, s->d_err);
-        SVFM_CUDA(cudaGetLastError());
-        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
-    }
-    uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
-    int cur = 0;  // items[cur] holds the current state from round 1 on
-    for (uint32_t r = 0; r < rounds; r++) {
-        const uint32_t first = r * T;
-        const uint32_t steps = remaining - first < T ? remaining - first : T;
-        const bool last = r + 1 == rounds;
-        const bool part = (!last || final_sort) && steps > 0;
-        // the last partition digit may be narrower than digit_bits: the histogram was taken on digit_bits bits, whose
-        // upper bits are then zero, so the wide digit sorts identically
-        const uint32_t nbins = nb_max;
-        SweepRoundIO<P, R> io{};
-        if (r == 0) { io.prefix = prefix.Current(); io.pay = pay.Current(); }
-        else io.items_in = items[cur];
-        if (last) {
-            io.sp_out = (P*)d_sp_work;
-            io.cnt_out = (P*)d_cnt_work;
-            io.idx_out = idx_work;
-            io.heavy_seen = s->d_counters;
-        } else {
-            io.items_out = items[r == 0 ? 0 : cur ^ 1];
-        }
-        io.hist = hist + (uint64_t)r * nb_max;
-        io.desc = (uint32_t*)s->sweep_desc.ptr;
-        io.tile_counter = tile_counters + r;
-        PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-        if (part) SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
-        const size_t smem = part ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 : 0;
-        auto launch = [&](auto kernel) -> int {
-            if (smem > 48 * 1024) SVFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ROUND_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-            uint64_t grid = n_tiles < (uint64_t)sms * per_sm ? n_tiles : (uint64_t)sms * per_sm;
-            kernel<<<(unsigned)grid, ROUND_THREADS, smem, s->stream>>>(dix, n, bits, bits * first, steps, nbins, io);
-            SVFM_CUDA(cudaGetLastError());
-            return SVFM_OK;
-        };
-        if (r == 0 && part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, true>);
-        else if (r == 0) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, false>);
-        else if (part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, true>);
-        else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, false>);
-        if (rc) return rc;
-        if (r > 0 && !last) cur ^= 1;
-    }
-    *idx_out = idx_work;
-    return SVFM_OK;
-}
-
-template <class P, int NPL, int VBITS>
-static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
-                            void* d_cnt_work, const uint32_t** idx_out) {
-    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
-    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
-}
-
-template <class P>
-struct WidenCounts {
-    const P* cnt;
-    uint64_t n;
-    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)cnt[i] : 0ull; }
-};
-
-template <class P, int NPL, int VBITS>
-static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) {
-    // out_offs[0..n] = exclusive prefix sums of the counts, widened to u64 (out_offs[n] = total)
-    WidenCounts<P> f{(const P*)d_cnt, n};
-    auto in = thrust::make_transform_iterator(thrust::counting_iterator<uint64_t>(0), f);
-    size_t temp = 0;
-    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp, in, d_out_offs, n + 1, s->stream));
-    int rc = s->cub_temp.reserve(temp);
-    if (rc) return rc;
-    PhaseTimer pt(s, SVFM_PHASE_SCAN, 2);
-    SVFM_CUDA(cub::DeviceScan::ExclusiveSum(s->cub_temp.ptr, temp, in, d_out_offs, n + 1, s->stream));
-    return SVFM_OK;
-}
-
 // Back to the caller's pattern order (count path): stable radix sort of (pattern index -> count) pairs; the
 // indices are a permutation of 0..n-1, so the sorted values ARE the counts in the caller's order.
-template <class P, int NPL, int VBITS>
+template <class P>
 static int run_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) {
     int rc;
     if ((rc = s->rec_key_alt.reserve(n * 4))) return rc;
@@ -630,51 +282,6 @@ static int run_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx,
     return SVFM_OK;
 }
 
-// LF-walk + sampled-SA lookup for every SA row of every pattern (SVFM_PHASE_LOCATE).
-template <class P, int NPL, int VBITS>
-static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
-                      const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
-    if (total == 0) return SVFM_OK;
-    const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    HeavyList<P> heavy{nullptr, nullptr, nullptr, nullptr, s->d_counters + 1, 0};
-    int rc;
-    if (heavy_seen) {
-        if ((rc = s->heavy_sp.reserve(heavy_seen * sizeof(P))) || (rc = s->heavy_cnt.reserve((heavy_seen + 1) * sizeof(P))) ||
-            (rc = s->heavy_obase.reserve(heavy_seen * sizeof(uint64_t))) || (rc = s->heavy_pat.reserve(heavy_seen * 4)) ||
-            (rc = s->heavy_offs.reserve((heavy_seen + 1) * sizeof(uint64_t))))
-            return rc;
-        heavy.sp = (P*)s->heavy_sp.ptr;
-        heavy.cnt = (P*)s->heavy_cnt.ptr;
-        heavy.obase = (uint64_t*)s->heavy_obase.ptr;
-        heavy.pat = (uint32_t*)s->heavy_pat.ptr;
-        heavy.capacity = heavy_seen;
-    }
-    {
-        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
-        const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS>, n, LOCATE_THREADS, s->ix->device);
-        locate_warp_kernel<P, NPL, VBITS><<<grid, LOCATE_THREADS, 0, s->stream>>>(
-            dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
-        SVFM_CUDA(cudaGetLastError());
-    }
-    if (!heavy_seen) return SVFM_OK;
-    // patterns with more than HEAVY_ROWS rows: one thread per row
-    if ((rc = run_scan<P, NPL, VBITS>(s, heavy_seen, heavy.cnt, (uint64_t*)s->heavy_offs.ptr))) return rc;
-    SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[2], (uint64_t*)s->heavy_offs.ptr + heavy_seen, sizeof(uint64_t),
-                              cudaMemcpyDeviceToHost, s->stream));
-    SVFM_CUDA(cudaStreamSynchronize(s->stream));
-    const uint64_t heavy_total = s->h_pinned[2];
-    const uint64_t blocks = (heavy_total + LOCATE_THREADS - 1) / LOCATE_THREADS;
-    if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
-    if (blocks) {
-        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
-        locate_rows_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
-            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
-            (P*)d_positions, d_rec_key);
-        SVFM_CUDA(cudaGetLastError());
-    }
-    return SVFM_OK;
-}
-
 struct MinOp {
     __host__ __device__ uint64_t operator()(uint64_t a, uint64_t b) const { return a < b ? a : b; }
 };
@@ -684,7 +291,7 @@ struct MinOp {
 // pattern index (LSD radix sort keeps SA-row order, or the ascending order of stage one, inside a pattern).
 // With want_offs the CSR offsets are rebuilt from the sorted pattern indices (run starts + reverse running
 // minimum); in direct mode they already exist.
-template <class P, int NPL, int VBITS>
+template <class P>
 static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, bool by_position, bool want_offs,
                                 uint64_t* d_out_offs, void** d_positions_inout) {
     int rc;
@@ -729,45 +336,94 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
     return SVFM_OK;
 }
 
-#define SVFM_DISPATCH_N(P, VB, FN, ...)                                     \
-    switch (t.planes) {                                                     \
-        case 2: return FN<P, 2, VB>(__VA_ARGS__);                           \
-        case 3: return FN<P, 3, VB>(__VA_ARGS__);                           \
-        case 4: return FN<P, 4, VB>(__VA_ARGS__);                           \
-        case 5: return FN<P, 5, VB>(__VA_ARGS__);                           \
-        case 6: return FN<P, 6, VB>(__VA_ARGS__);                           \
-        default: return SVFM_ERR_BAD_TYPE;                                  \
-    }
-#define SVFM_DISPATCH_V(P, FN, ...)                                         \
-    switch (t.vec_bits) {                                                   \
-        case 32: SVFM_DISPATCH_N(P, 32, FN, __VA_ARGS__)                    \
-        case 64: SVFM_DISPATCH_N(P, 64, FN, __VA_ARGS__)                    \
-        case 128: SVFM_DISPATCH_N(P, 128, FN, __VA_ARGS__)                  \
-        default: return SVFM_ERR_BAD_TYPE;                                  \
-    }
-#ifdef SVFM_ONLY_CFG1  /* developer builds: only FmIndex<u32, Block3<u64>> (seconds instead of minutes to compile) */
-#undef SVFM_DISPATCH_V
-#define SVFM_DISPATCH_V(P, FN, ...) \
-    if (t.vec_bits == 64 && t.planes == 3) return FN<P, 3, 64>(__VA_ARGS__); \
-    return SVFM_ERR_BAD_TYPE;
-#endif
-#define SVFM_DISPATCH(FN, ...)                                              \
-    do {                                                                    \
-        const svfm_type& t = s->ix->type;                                   \
-        if (t.pos_bits == 32) { SVFM_DISPATCH_V(uint32_t, FN, __VA_ARGS__) } \
-        else { SVFM_DISPATCH_V(uint64_t, FN, __VA_ARGS__) }                 \
-    } while (0)
-
-static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits, void* d_sp_work, void* d_cnt_work) { SVFM_DISPATCH(run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work); }
-static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) { SVFM_DISPATCH(run_search_sweep, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out); }
-static int build_ext_table(svfm_index* ix) {
-    struct { svfm_index* ix; } shim{ix}, *s = &shim;
-    SVFM_DISPATCH(run_build_ext, ix, 0);
+// Front of the sweep search, independent of the index type: pack_sweep_kernel + radix sort by table index.
+template <class R>
+int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, uint32_t rounds, SweepPre* out) {
+    const svfm_index* ix = s->ix;
+    using Pay = SweepPay<R>;
+    const uint64_t n = pb.n;
+    const uint32_t len = pb.fixed_len, bits = plan.bits;
+    const uint32_t digit_bits = bits * plan.steps_per_round, nb_max = 1u << digit_bits;
+    int rc;
+    if ((rc = s->keys0.reserve(n * 4)) || (rc = s->keys1.reserve(n * 4)) || (rc = s->pay0.reserve(n * sizeof(Pay))) ||
+        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + rounds + 64) * 4)))
+        return rc;
+    cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
+    cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
+    uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
+    size_t t1 = 0;
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
+    if ((rc = s->cub_temp.reserve(t1))) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits + 7) / 8);
+    SVFM_CUDA(cudaMemsetAsync(hist, 0, ((uint64_t)rounds * nb_max + rounds + 64) * 4, s->stream));
+    const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
+    DevSyms syms;
+    syms.symbol_count = ix->L.symbol_count;
+    syms.s_eff = ix->symbols_present;
+    std::memcpy(syms.sym_rank, ix->sym_rank, 64);
+    const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) + (size_t)rounds * nb_max * 4;
+    SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;
+    if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
+    pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, plan.m, prefix.Current(), pay.Current(),
+                                                                        digit_bits, rounds, hist, s->d_err);
+    SVFM_CUDA(cudaGetLastError());
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
+    out->prefix = prefix.Current();
+    out->pay = pay.Current();
+    out->hist = hist;
+    return SVFM_OK;
 }
-static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) { SVFM_DISPATCH(run_scan, s, n, d_cnt, d_out_offs); }
-static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) { SVFM_DISPATCH(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out); }
-static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) { SVFM_DISPATCH(run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key); }
-static int dispatch_sortback_records(svfm_session* s, uint64_t n, uint64_t total, bool by_position, bool want_offs, uint64_t* d_out_offs, void** d_positions) { SVFM_DISPATCH(run_sortback_records, s, n, total, by_position, want_offs, d_out_offs, d_positions); }
+template int run_sweep_presort<uint32_t>(svfm_session*, const PatternBatch&, const SortPlan&, uint32_t, SweepPre*);
+template int run_sweep_presort<uint64_t>(svfm_session*, const PatternBatch&, const SortPlan&, uint32_t, SweepPre*);
+
+// ---- dispatch: kernel-launching stages go through the per-(P, Vector) tables (inst_p*_v*.cu); the stages that only
+// depend on the position width (radix sorts, scans) are instantiated here ------------------------------------------
+static const TypeOps* type_ops(const svfm_type& t) {
+    const bool p32 = t.pos_bits == 32;
+    switch (t.vec_bits) {
+        case 32: return p32 ? &ops_p32_v32 : &ops_p64_v32;
+        case 64: return p32 ? &ops_p32_v64 : &ops_p64_v64;
+        case 128: return p32 ? &ops_p32_v128 : &ops_p64_v128;
+        default: return nullptr;
+    }
+}
+#define SVFM_BY_POS(FN, ...) (s->ix->type.pos_bits == 32 ? FN<uint32_t>(__VA_ARGS__) : FN<uint64_t>(__VA_ARGS__))
+
+static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
+                           void* d_sp_work, void* d_cnt_work) {
+    const TypeOps* ops = type_ops(s->ix->type);
+    return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work) : SVFM_ERR_BAD_TYPE;
+}
+static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
+                                 void* d_cnt_work, const uint32_t** idx_out) {
+    const TypeOps* ops = type_ops(s->ix->type);
+    return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out) : SVFM_ERR_BAD_TYPE;
+}
+static int build_ext_table(svfm_index* ix) {
+    const TypeOps* ops = type_ops(ix->type);
+    return ops ? ops->build_ext(ix->type.planes, ix, g_ext_bits.load()) : SVFM_ERR_BAD_TYPE;
+}
+static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
+                           const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
+    const TypeOps* ops = type_ops(s->ix->type);
+    return ops ? ops->locate(s->ix->type.planes, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key)
+               : SVFM_ERR_BAD_TYPE;
+}
+static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) {
+    return SVFM_BY_POS(run_scan, s, n, d_cnt, d_out_offs);
+}
+static int dispatch_sortback_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) {
+    return SVFM_BY_POS(run_sortback_counts, s, n, idx, d_cnt_work, d_counts_out);
+}
+static int dispatch_sortback_records(svfm_session* s, uint64_t n, uint64_t total, bool by_position, bool want_offs,
+                                     uint64_t* d_out_offs, void** d_positions) {
+    return SVFM_BY_POS(run_sortback_records, s, n, total, by_position, want_offs, d_out_offs, d_positions);
+}
 
 static int err_from_bits(int bits) {
     if (bits & ERRBIT_EMPTY_PATTERN) return SVFM_ERR_EMPTY_PATTERN;
@@ -871,7 +527,7 @@ static int check_host_patterns(const uint8_t* pats, const uint64_t* offs, uint64
 // ---------------------------------------------------------------------------------------------
 static std::atomic<uint64_t> g_chunk_patterns{[] {
     const char* e = std::getenv("SVFM_CHUNK");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(16u << 20);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(8u << 20);
 }()};
 static std::atomic<uint64_t> g_host_workers{[] {
     const char* e = std::getenv("SVFM_WORKERS");
@@ -889,23 +545,39 @@ __global__ void add_base_kernel(uint64_t* __restrict__ v, uint64_t n, uint64_t b
 }
 
 struct ChunkPlan {
-    uint64_t n = 0, chunk = 0, chunks = 0;
-    uint64_t begin(uint64_t c) const { return c * chunk; }
-    uint64_t end(uint64_t c) const { return (c + 1) * chunk < n ? (c + 1) * chunk : n; }
+    uint64_t n = 0, chunks = 0;
+    std::vector<uint64_t> bounds;  // chunks + 1 pattern indices
+    uint64_t begin(uint64_t c) const { return bounds[c]; }
+    uint64_t end(uint64_t c) const { return bounds[c + 1]; }
 };
 
+// Even chunks of about SVFM_TUNE_CHUNK patterns, every boundary a multiple of 256 patterns (chunk copies stay 16-byte
+// aligned for the TMA staging).  The LAST chunk is halved repeatedly (down to ~1 Mi patterns): the upload stream is the
+// bottleneck of a host batch, so what remains after the last byte has arrived -- kernels + download of the final
+// chunk -- should be small.
 static ChunkPlan plan_chunks(uint64_t n) {
     ChunkPlan p;
     p.n = n;
     uint64_t c = g_chunk_patterns.load();
     if (c == 0) c = n;
-    p.chunks = (n + c - 1) / c;
-    if (p.chunks == 0) p.chunks = 1;
-    p.chunk = (n + p.chunks - 1) / p.chunks;  // even chunks ...
-    if (p.chunks > 1) p.chunk = (p.chunk + 255) & ~(uint64_t)255;  // ... whose device copies stay 16-byte aligned (TMA staging)
-    if (p.chunk == 0) p.chunk = 1;
-    p.chunks = (n + p.chunk - 1) / p.chunk;
-    if (p.chunks == 0) p.chunks = 1;
+    uint64_t k = (n + c - 1) / c;
+    if (k == 0) k = 1;
+    uint64_t chunk = (n + k - 1) / k;
+    if (k > 1) chunk = (chunk + 255) & ~(uint64_t)255;
+    if (chunk == 0) chunk = 1;
+    p.bounds.push_back(0);
+    for (uint64_t at = chunk; at < n; at += chunk) p.bounds.push_back(at);
+    static const bool taper = [] { const char* e = std::getenv("SVFM_TAPER"); return e ? atoi(e) != 0 : true; }();
+    if (k > 1 && taper) {
+        uint64_t a = p.bounds.back();
+        while (n - a > (2u << 20)) {
+            const uint64_t half = (((n - a) / 2) + 255) & ~(uint64_t)255;
+            a += half;
+            p.bounds.push_back(a);
+        }
+    }
+    p.bounds.push_back(n);
+    p.chunks = p.bounds.size() - 1;
     return p;
 }
 

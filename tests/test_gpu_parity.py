@@ -340,4 +340,4 @@ def test_chunked_host_pipeline(oracle, fm):
             with pytest.raises(fm.EmptyPattern):
                 gpu.locate_batch(var[:5000] + [b""] + var[5000:6000])
     finally:
-        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 16 << 20)
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
