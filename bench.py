@@ -324,7 +324,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         Ke = args.e2e_steps or K
-        n_host = min(n_distinct, 3)
+        n_host = min(n_distinct, 2)
         cap = B + B // 4 + 1024
         h_pats = []
         for s in range(n_host):

@@ -213,7 +213,8 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
     p.bits = (uint32_t)bits_for(S);
     if (p.bits == 0) p.bits = 1;
     if (n > 0xffffffffull) return p;
-    if (!pb.offs && ix->ext_m && n >= g_sweep_min.load() && pb.fixed_len >= ix->ext_m &&
+    if (!pb.offs && ix->ext_m && n >= g_sweep_min.load() && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
+        pb.fixed_len >= ix->ext_m &&
         (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits <= 64) {
         p.sweep = true;
         p.m = ix->ext_m;

@@ -341,3 +341,43 @@ def test_chunked_host_pipeline(oracle, fm):
                 gpu.locate_batch(var[:5000] + [b""] + var[5000:6000])
     finally:
         L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
+
+
+def test_concurrent_callers(oracle, fm):
+    """`FmIndex` is Send + Sync in the reference (immutable &self queries): concurrent batch calls on ONE handle from
+    several host threads must each get their own stream + scratch arena and the right answers."""
+    import threading
+    po = oracle
+    rng = np.random.default_rng(5)
+    n = 300_000
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)]
+    table, sc = po.encoding_table([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
+    t = po.IndexType(32, 3, 64, True)
+    blob = po.build_blob(t, text, sc, table, 3, 2)
+    ora = po.OracleFmIndex.load(blob, t)
+    gpu = fm.FmIndex.load(blob, fm.IndexType(32, 3, 64, True))
+    jobs = []
+    for j in range(6):
+        ln = 6 + 3 * j
+        starts = rng.integers(0, n - ln, size=40_000)
+        pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
+        pats[::9, 1] = ord("C")
+        jobs.append((pats, ora.locate_batch(pats, threads=4)))
+    errors = []
+
+    def worker(j):
+        try:
+            pats, (oc, oo, op_, _) = jobs[j]
+            for _ in range(3):
+                assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc)
+                offs, pos = gpu.locate_batch(pats)
+                assert np.array_equal(offs, oo) and np.array_equal(pos, op_)
+        except Exception as e:  # noqa: BLE001
+            errors.append((j, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
