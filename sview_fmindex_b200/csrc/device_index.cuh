@@ -67,6 +67,19 @@ template <> struct VecTraits<128> { using W = uint64_t; static constexpr int WOR
 __device__ __forceinline__ int popc_w(uint32_t x) { return __popc(x); }
 __device__ __forceinline__ int popc_w(uint64_t x) { return __popcll(x); }
 
+// popcount of the `rem` most significant bits of x, rem in [0, width]: x >> (width - rem) with PTX shift semantics
+// (a shift by the full width gives 0, so rem == 0 needs no branch -- in C++ that shift would be undefined).
+__device__ __forceinline__ uint32_t popc_top(uint32_t x, uint32_t rem) {
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(32u - rem));
+    return (uint32_t)__popc(r);
+}
+__device__ __forceinline__ uint32_t popc_top(uint64_t x, uint32_t rem) {
+    unsigned long long r;
+    asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"((unsigned long long)x), "r"(64u - rem));
+    return (uint32_t)__popcll(r);
+}
+
 template <int NPL, int VBITS>
 struct Block {
     using T = VecTraits<VBITS>;
@@ -123,13 +136,11 @@ struct Block {
     __device__ __forceinline__ static uint32_t prefix_count(const W (&m)[T::WORDS], uint32_t rem) {
         if (T::WORDS == 1) {
             // count_bits >>= BLOCK_LEN - rem; count_ones()   (block3.rs:53-54); rem == 0 never shifts
-            return rem ? (uint32_t)popc_w((W)(m[0] >> (T::WBITS - rem))) : 0u;
+            return popc_top(m[0], rem);
         } else {
             uint32_t r0 = rem < 64u ? rem : 64u;  // symbols taken from word 0
             uint32_t r1 = rem - r0;               // symbols taken from word 1
-            uint32_t c = r0 ? (uint32_t)popc_w((W)(m[0] >> (64u - r0))) : 0u;
-            c += r1 ? (uint32_t)popc_w((W)(m[1] >> (64u - r1))) : 0u;
-            return c;
+            return popc_top(m[0], r0) + popc_top(m[1], r1);
         }
     }
 

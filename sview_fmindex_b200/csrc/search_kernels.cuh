@@ -294,17 +294,26 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     const bool tma_ok = (reinterpret_cast<uintptr_t>(pb.pats) & 15u) == 0;  // tile_bytes = 256 * len is a multiple of 16
     int errbits = 0;
 
+    const bool words_ok = (len & 3u) == 0;  // a pattern then starts on a 4-byte boundary of the staged tile
     auto pack_one = [&](const uint8_t* p, uint64_t i) {
-        uint32_t e = 0, mult = 1;
-        uint32_t flags = 0;
+        uint32_t e = 0, mult = 1, flags = 0, word = 0;
         R rest = 0;
-        for (uint32_t j = 0; j < len; j++) {  // j-th symbol from the end
-            const uint32_t v = s_lut[p[pb.reversed ? j : len - 1 - j]];
+        for (uint32_t f = 0; f < len; f++) {  // f-th stored byte
+            uint32_t byte;
+            if (words_ok) {
+                if ((f & 3u) == 0) word = reinterpret_cast<const uint32_t*>(p)[f >> 2];
+                byte = (word >> ((f & 3u) * 8u)) & 0xffu;
+            } else {
+                byte = p[f];
+            }
+            const uint32_t v = s_lut[byte];
             flags |= v & 0x8000u;
+            const uint32_t j = pb.reversed ? f : len - 1 - f;  // j-th symbol from the end of the pattern
             if (j < m) {
                 flags |= v & 0x4000u;
-                e += ((v >> 8) & 0x3fu) * mult;
-                mult *= syms.s_eff;
+                const uint32_t r = (v >> 8) & 0x3fu;
+                if (pb.reversed) { e += r * mult; mult *= syms.s_eff; }  // j ascends: least significant digit first
+                else e = e * syms.s_eff + r;                             // j descends: Horner
             } else {
                 rest |= (R)(v & 0xffu) << (bits * (j - m));
             }

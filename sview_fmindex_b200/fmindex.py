@@ -137,7 +137,12 @@ def _as_u8(buf) -> np.ndarray:
 
 
 def _pack_patterns(patterns):
-    """-> (bytes u8[], offs u64[n+1] or None, n, fixed_len).  A 2-D uint8 array is a fixed-length batch."""
+    """-> (bytes u8[], offs u64[n+1] or None, n, fixed_len).  A 2-D uint8 array is a fixed-length batch; a
+    (bytes u8[], offs u64[n+1]) tuple is taken as is (the C ABI's own form)."""
+    if isinstance(patterns, tuple) and len(patterns) == 2 and isinstance(patterns[1], np.ndarray):
+        data = np.ascontiguousarray(patterns[0], dtype=np.uint8).reshape(-1)
+        offs = np.ascontiguousarray(patterns[1], dtype=np.uint64)
+        return data, offs, len(offs) - 1, 0
     if isinstance(patterns, np.ndarray) and patterns.ndim == 2:
         p = np.ascontiguousarray(patterns, dtype=np.uint8)
         return p.reshape(-1), None, p.shape[0], p.shape[1]
