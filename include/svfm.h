@@ -165,16 +165,22 @@ void svfm_host_free(void* p);
 /* Process-wide tuning knobs; results never depend on any of them.
  * SVFM_TUNE_SORT_MIN : batches with at least this many patterns (that do not qualify for the sweep search) are
  *                      locality-sorted by their trailing symbols before the search kernel (0 = always,
- *                      UINT64_MAX = never; default 131072; env SVFM_SORT_MIN).
+ *                      UINT64_MAX = never; default SVFM_TUNE_AUTO = never when the index has an extended k-mer table
+ *                      -- nothing is left to share after the lookup -- else 131072; env SVFM_SORT_MIN).
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
  *                      pipeline upload / kernels / download (0 = one chunk; default 8 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
- *                      kept sorted by SA position and moves through the index as streams (default 1 Mi; env
- *                      SVFM_SWEEP_MIN).
+ *                      kept sorted by SA position and moves through the index as streams (default 3 Mi, the measured
+ *                      break-even with the plain search kernel on a 1 Gbp index; env SVFM_SWEEP_MIN).
  * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries, derived
  *                      from the blob at load (0 = none; default 24 = 128 MiB for u32 positions; env SVFM_EXT_BITS).
- * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS). */
-enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4 };
+ * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS).
+ * SVFM_TUNE_ILV      : indexes loaded from now on also get an interleaved copy of the occ data -- block q and checkpoint
+ *                      row q in one aligned 32/64/128-byte slot -- which the gather-bound kernels read instead of the two
+ *                      blob sections (1 = build, the default; 0 = search the blob in place only; env SVFM_ILV). */
+enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
+       SVFM_TUNE_ILV = 5 };
+#define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */
 uint64_t svfm_launch_count(void);     /* kernels launched by this library since process start */

@@ -33,6 +33,8 @@ SVFM_TUNE_CHUNK = 1
 SVFM_TUNE_SWEEP_MIN = 2
 SVFM_TUNE_EXT_BITS = 3
 SVFM_TUNE_WORKERS = 4
+SVFM_TUNE_ILV = 5
+SVFM_TUNE_AUTO = 0xFFFFFFFFFFFFFFFE
 SVFM_REVERSED = 1
 SVFM_SORTED = 2
 

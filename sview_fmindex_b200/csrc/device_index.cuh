@@ -32,6 +32,12 @@ struct DevIndex {
     uint32_t s_eff;                   // symbols that occur in the text
     uint8_t sym_rank[64];             // symbol index -> rank among the occurring symbols, 0xff = never occurs
     uint8_t present[64];              // rank -> symbol index
+    // interleaved occ copy derived from the blob at load (opt-out SVFM_TUNE_ILV): entry q =
+    // { block q | checkpoint row q } in ONE aligned slot of ilv_stride bytes, so that a rank query costs one DRAM fetch
+    // instead of two or three.  Used by the gather-bound kernels (search_kernel, locate); NULL = not built.
+    const uint8_t* ilv;
+    uint32_t ilv_stride;              // bytes per entry (32, 64, 128 or a multiple of 128)
+    uint32_t ilv_ck_off;              // byte offset of the checkpoint row inside an entry
 };
 
 // the symbol maps alone (kernels that do not touch the index arrays)
@@ -114,6 +120,31 @@ struct Block {
             }
         } else {
             const W* base = reinterpret_cast<const W*>(blocks) + q * (uint64_t)NW;
+#pragma unroll
+            for (int v = 0; v < NPL; v++) w[v][0] = ld_gather<W>(base + v);
+        }
+    }
+
+    // Same block from the interleaved copy: the entry starts on a 16-byte boundary, so no window shifting.
+    __device__ __forceinline__ void load_aligned(const uint8_t* entry) {
+        constexpr int NW = NPL * T::WORDS;
+        if constexpr (sizeof(W) == 8) {
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(entry);
+            unsigned long long raw[NW + 1];
+#pragma unroll
+            for (int c = 0; c < NW / 2; c++) {
+                const ulonglong2 v = __ldg(p + c);
+                raw[2 * c] = v.x;
+                raw[2 * c + 1] = v.y;
+            }
+            if (NW & 1) raw[NW - 1] = __ldg(reinterpret_cast<const unsigned long long*>(entry) + (NW - 1));
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                if (T::WORDS == 1) w[i][0] = raw[i];
+                else w[i / 2][(i & 1) ? 0 : T::WORDS - 1] = raw[i];  // u128: low half first in memory
+            }
+        } else {
+            const W* base = reinterpret_cast<const W*>(entry);
 #pragma unroll
             for (int v = 0; v < NPL; v++) w[v][0] = ld_gather<W>(base + v);
         }

@@ -38,6 +38,8 @@ struct svfm_index {
     uint32_t ext_m = 0;            // extended k-mer table: symbols resolved per lookup (0 = no table)
     uint64_t ext_entries = 0;
     void* d_ext = nullptr;         // P[2 * ext_entries]
+    uint8_t* d_ilv = nullptr;      // interleaved occ copy (blocks_len entries of ilv_stride bytes), or NULL
+    uint32_t ilv_stride = 0, ilv_ck_off = 0;
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
     std::vector<svfm_uploader*> up_pool;  // idle uploaders
@@ -102,6 +104,9 @@ static DevIndex<P> make_dev_index(const svfm_index* ix) {
     d.s_eff = ix->symbols_present;
     std::memcpy(d.sym_rank, ix->sym_rank, 64);
     std::memcpy(d.present, ix->present, 64);
+    d.ilv = ix->d_ilv;
+    d.ilv_stride = ix->ilv_stride;
+    d.ilv_ck_off = ix->ilv_ck_off;
     return d;
 }
 
@@ -189,7 +194,9 @@ template <class P, int NPL, int VBITS>
 static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
                       void* d_sp_work, void* d_cnt_work) {
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
-    const int grid = resident_grid(search_kernel<P, NPL, VBITS>, pb.n, SEARCH_THREADS, s->ix->device);
+    const bool ilv = dix.ilv != nullptr;
+    const int grid = ilv ? resident_grid(search_kernel<P, NPL, VBITS, true>, pb.n, SEARCH_THREADS, s->ix->device)
+                         : resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
     SearchIO<P> io{};
     io.keys = keys;
     io.idx = idx;
@@ -199,7 +206,8 @@ static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* k
     io.heavy_seen = s->d_counters;
     io.err = s->d_err;
     PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-    search_kernel<P, NPL, VBITS><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+    if (ilv) search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+    else search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
     SVFM_CUDA(cudaGetLastError());
     return SVFM_OK;
 }
@@ -382,9 +390,15 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
     }
     {
         PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
-        const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS>, n, LOCATE_THREADS, s->ix->device);
-        locate_warp_kernel<P, NPL, VBITS><<<grid, LOCATE_THREADS, 0, s->stream>>>(
-            dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+        if (dix.ilv) {
+            const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS, true>, n, LOCATE_THREADS, s->ix->device);
+            locate_warp_kernel<P, NPL, VBITS, true><<<grid, LOCATE_THREADS, 0, s->stream>>>(
+                dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+        } else {
+            const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS, false>, n, LOCATE_THREADS, s->ix->device);
+            locate_warp_kernel<P, NPL, VBITS, false><<<grid, LOCATE_THREADS, 0, s->stream>>>(
+                dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+        }
         SVFM_CUDA(cudaGetLastError());
     }
     if (!heavy_seen) return SVFM_OK;
@@ -398,7 +412,12 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
     if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
     if (blocks) {
         PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
-        locate_rows_kernel<P, NPL, VBITS><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
+        if (dix.ilv)
+            locate_rows_kernel<P, NPL, VBITS, true><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
+            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
+            (P*)d_positions, d_rec_key);
+        else
+            locate_rows_kernel<P, NPL, VBITS, false><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
             dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
             (P*)d_positions, d_rec_key);
         SVFM_CUDA(cudaGetLastError());

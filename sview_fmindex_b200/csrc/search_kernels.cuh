@@ -24,7 +24,7 @@ constexpr uint32_t HEAVY_ROWS = 1024;  // patterns with more SA rows than this a
 // All four gathers (2 checkpoint words + 2 blocks) are issued before the first use; when both ends
 // fall into the same block (the common case once the interval is short) the block and the
 // checkpoint word are fetched once.
-template <class P, int NPL, int VBITS>
+template <class P, int NPL, int VBITS, bool ILV = false>
 __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, const P* __restrict__ s_count, uint32_t sym,
                                               P& sp, P& ep) {
     uint64_t q0, q1;
@@ -35,17 +35,34 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, const P* __
     Block<NPL, VBITS> b0;
     typename Block<NPL, VBITS>::W m[VecTraits<VBITS>::WORDS];
     if (q0 == q1) {
-        const P ck = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
-        b0.load(ix.blocks, q0);
+        P ck;
+        if constexpr (ILV) {
+            const uint8_t* e0 = ix.ilv + q0 * ix.ilv_stride;
+            ck = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
+            b0.load_aligned(e0);
+        } else {
+            ck = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
+            b0.load(ix.blocks, q0);
+        }
         b0.match_mask(sym, m);
         sp = c + ck + (P)Block<NPL, VBITS>::prefix_count(m, r0);
         ep = c + ck + (P)Block<NPL, VBITS>::prefix_count(m, r1);
     } else {
         Block<NPL, VBITS> b1;
-        const P ck0 = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
-        const P ck1 = ld_gather<P>(ix.rank_checkpoints + q1 * ix.symbol_count + sym);
-        b0.load(ix.blocks, q0);
-        b1.load(ix.blocks, q1);
+        P ck0, ck1;
+        if constexpr (ILV) {
+            const uint8_t* e0 = ix.ilv + q0 * ix.ilv_stride;
+            const uint8_t* e1 = ix.ilv + q1 * ix.ilv_stride;
+            ck0 = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
+            ck1 = ld_gather<P>(reinterpret_cast<const P*>(e1 + ix.ilv_ck_off) + sym);
+            b0.load_aligned(e0);
+            b1.load_aligned(e1);
+        } else {
+            ck0 = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
+            ck1 = ld_gather<P>(ix.rank_checkpoints + q1 * ix.symbol_count + sym);
+            b0.load(ix.blocks, q0);
+            b1.load(ix.blocks, q1);
+        }
         b0.match_mask(sym, m);
         sp = c + ck0 + (P)Block<NPL, VBITS>::prefix_count(m, r0);
         b1.match_mask(sym, m);
@@ -103,7 +120,7 @@ struct SearchIO {
 // Seeding: patterns at least ext_m symbols long start from the extended k-mer table (one lookup resolves the last
 // ext_m symbols -- the device twin of the reference's kLTS, count_array.rs:203-233, with a longer k chosen for
 // HBM instead of for a CPU cache); shorter ones use the blob's own kLTS.
-template <class P, int NPL, int VBITS>
+template <class P, int NPL, int VBITS, bool ILV>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io) {
     __shared__ uint8_t s_table[256];
@@ -174,7 +191,7 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
             // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
             while (sp < ep && pi > 0) {
                 pi -= 1;
-                backward_step<P, NPL, VBITS>(ix, s_count, sym_at(pi), sp, ep);
+                backward_step<P, NPL, VBITS, ILV>(ix, s_count, sym_at(pi), sp, ep);
             }
         }
         const P cnt = (P)(ep - sp);
@@ -183,6 +200,23 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
         if (io.heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);  // rare: sizes the heavy list
     }
     if (errbits) atomicOr(io.err, errbits);
+}
+
+// ---- interleaved occ copy (built once per index at load) ----------------------------------
+// entry q of `dst` (stride bytes) = block q (block_bytes) at offset 0, checkpoint row q (row_bytes) at offset ck_off.
+// Pure byte movement in 4-byte words; every size involved is a multiple of 4.
+static __global__ void ilv_build_kernel(const uint32_t* __restrict__ blocks, uint32_t block_words, const uint32_t* __restrict__ rows,
+                                        uint32_t row_words, uint32_t* __restrict__ dst, uint32_t stride_words, uint32_t ck_off_words,
+                                        uint64_t entries) {
+    const uint64_t total = entries * stride_words;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t q = t / stride_words;
+        const uint32_t w = (uint32_t)(t - q * stride_words);
+        uint32_t v = 0;
+        if (w < block_words) v = blocks[q * block_words + w];
+        else if (w >= ck_off_words && w < ck_off_words + row_words) v = rows[q * row_words + (w - ck_off_words)];
+        dst[t] = v;
+    }
 }
 
 // ---- extended k-mer table (built once per index at load) --------------------------------------------------------
@@ -613,7 +647,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
 // FmIndex::write_locations_to_buffer (locate/mod.rs:14-37) for ONE SA row: LF-walk to the nearest
 // sampled row (BwmView::get_pre_rank_and_symidx, bwm/mod.rs:217-236), then
 // SuffixArrayView::get_location_of (suffix_array/mod.rs:100-105).
-template <class P, int NPL, int VBITS>
+template <class P, int NPL, int VBITS, bool ILV>
 __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restrict__ s_count, P pos) {
     P offset = 0;
     for (;;) {
@@ -633,9 +667,18 @@ __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restri
         uint32_t rem;
         rank_addr<P, VBITS>(ix, pos, q, rem);
         Block<NPL, VBITS> b;
-        b.load(ix.blocks, q);
-        const uint32_t s = b.symidx_of(rem);
-        const P ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
+        P ck;
+        uint32_t s;
+        if constexpr (ILV) {
+            const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
+            b.load_aligned(e);
+            s = b.symidx_of(rem);
+            ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
+        } else {
+            b.load(ix.blocks, q);
+            s = b.symidx_of(rem);
+            ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
+        }
         pos = (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
         offset += 1;
     }
@@ -662,7 +705,7 @@ struct HeavyList {
 // counts, then each lane finds the owner of its row with a shuffle binary search), so a pattern with many
 // rows does not serialise one lane.  Patterns with more than HEAVY_ROWS rows are deferred to
 // locate_rows_kernel through the heavy list.
-template <class P, int NPL, int VBITS>
+template <class P, int NPL, int VBITS, bool ILV>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
                    const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
@@ -697,7 +740,7 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
         if (__all_sync(full, c <= 1u)) {
             // common case: at most one row per pattern, no redistribution needed
             if (c) {
-                positions[obase] = locate_row<P, NPL, VBITS>(ix, s_count, sp);
+                positions[obase] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp);
                 if (rec_key) rec_key[obase] = pat;
             }
             continue;
@@ -726,7 +769,7 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
             const uint32_t opat = __shfl_sync(full, pat, o);
             if (r < total) {
                 const uint32_t j = r - e;
-                positions[oo + j] = locate_row<P, NPL, VBITS>(ix, s_count, (P)(osp + (P)j));
+                positions[oo + j] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j));
                 if (rec_key) rec_key[oo + j] = opat;
             }
         }
@@ -736,7 +779,7 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
 // Row-parallel locate for the heavy list: one thread per SA row; row t belongs to the entry h with
 // offs[h] <= t < offs[h+1].  The per-block window of candidate entries is found once with two binary
 // searches; each thread then searches only that window.
-template <class P, int NPL, int VBITS>
+template <class P, int NPL, int VBITS, bool ILV>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_t* __restrict__ offs,
                    const uint64_t* __restrict__ obase, const uint32_t* __restrict__ pat, uint64_t n, uint64_t total,
@@ -766,7 +809,7 @@ locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_
     const uint64_t j = t - __ldg(offs + lo);
     const P row = (P)(__ldg(sp + lo) + (P)j);
     const uint64_t dst = __ldg(obase + lo) + j;
-    positions[dst] = locate_row<P, NPL, VBITS>(ix, s_count, row);
+    positions[dst] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, row);
     if (rec_key) rec_key[dst] = __ldg(pat + lo);
 }
 

@@ -72,6 +72,7 @@ static int finish_load(svfm_index* ix) {
 }
 
 static int build_ext_table(svfm_index* ix);
+static int build_ilv_table(svfm_index* ix);
 
 static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int device, bool src_on_device,
                        svfm_index** out, uint64_t err_detail[2]) {
@@ -118,7 +119,9 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
     }
     rc = finish_load(ix);
     if (rc == SVFM_OK) rc = build_ext_table(ix);
+    if (rc == SVFM_OK) rc = build_ilv_table(ix);
     if (rc) {
+        if (ix->d_ilv) cudaFree(ix->d_ilv);
         if (ix->d_ext) cudaFree(ix->d_ext);
         cudaFree(ix->d_alloc);
         delete ix;
@@ -191,16 +194,27 @@ struct SessionLease {
 
 static std::atomic<uint64_t> g_sort_min{[] {
     const char* e = std::getenv("SVFM_SORT_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 17);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
-static uint64_t sort_min_patterns() { return g_sort_min.load(); }
+// AUTO: with the extended table the first m symbols cost one lookup and every later step is a private row, so a
+// locality sort has nothing left to share (measured: 0.16 ms unsorted vs 0.32 ms sorted for 3*10^5 20-mers, 176 vs 164 M
+// reads/s for 150 bp reads); without the table the early steps still profit from it.
+static uint64_t sort_min_patterns(const svfm_index* ix) {
+    const uint64_t v = g_sort_min.load();
+    if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
+    return ix->ext_m ? ~(uint64_t)0 : (uint64_t)(1u << 17);
+}
 static std::atomic<uint64_t> g_sweep_min{[] {
     const char* e = std::getenv("SVFM_SWEEP_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(1u << 20);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(3u << 20);
 }()};
 static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
     const char* e = std::getenv("SVFM_EXT_BITS");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)24;
+}()};
+static std::atomic<uint64_t> g_ilv{[] {  // build the interleaved occ copy at load
+    const char* e = std::getenv("SVFM_ILV");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
 static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once more after the last round
     const char* e = std::getenv("SVFM_SWEEP_FINAL_SORT");
@@ -228,7 +242,7 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
         p.steps_per_round = t < 1 ? 1 : (t > 3 && !t_env ? 3 : t);
         return p;
     }
-    if (n < sort_min_patterns()) return p;
+    if (n < sort_min_patterns(ix)) return p;
     // Sort on as many trailing symbols as it takes to tell the occ blocks apart: log_{S_eff}(blocks) + 1
     // symbols, S_eff = symbols that actually occur in the text (count_array).
     const double s_eff = ix->symbols_present > 1 ? (double)ix->symbols_present : 2.0;
@@ -404,6 +418,34 @@ static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const 
                                  void* d_cnt_work, const uint32_t** idx_out) {
     const TypeOps* ops = type_ops(s->ix->type);
     return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out) : SVFM_ERR_BAD_TYPE;
+}
+// Interleaved occ copy: { block q | checkpoint row q } per aligned slot.  Derived from the blob, bytes only.
+static int build_ilv_table(svfm_index* ix) {
+    if (!g_ilv.load()) return SVFM_OK;
+    const Layout& L = ix->L;
+    const uint64_t P = ix->type.pos_bits / 8;
+    const uint64_t block_bytes = (uint64_t)ix->type.planes * ix->type.vec_bits / 8;
+    const uint64_t row_bytes = (uint64_t)L.bwm_symbol_count * P;
+    const uint64_t ck_off = (block_bytes + P - 1) / P * P;
+    const uint64_t raw = ck_off + row_bytes;
+    uint64_t stride = raw <= 32 ? 32 : raw <= 64 ? 64 : (raw + 127) / 128 * 128;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, L.blocks_len * stride);
+    if (e != cudaSuccess) {  // not enough memory for the copy: keep searching the blob in place
+        (void)cudaGetLastError();
+        return SVFM_OK;
+    }
+    ilv_build_kernel<<<grid_for(L.blocks_len * (stride / 4), 256, ix->device), 256>>>(
+        reinterpret_cast<const uint32_t*>(ix->d_blob + L.off_blocks), (uint32_t)(block_bytes / 4),
+        reinterpret_cast<const uint32_t*>(ix->d_blob + L.off_rank_checkpoints), (uint32_t)(row_bytes / 4), (uint32_t*)d,
+        (uint32_t)(stride / 4), (uint32_t)(ck_off / 4), L.blocks_len);
+    g_launches++;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); SVFM_CUDA(e); }
+    ix->d_ilv = (uint8_t*)d;
+    ix->ilv_stride = (uint32_t)stride;
+    ix->ilv_ck_off = (uint32_t)ck_off;
+    return SVFM_OK;
 }
 static int build_ext_table(svfm_index* ix) {
     const TypeOps* ops = type_ops(ix->type);
@@ -950,6 +992,7 @@ void svfm_free(svfm_index* ix) {
         delete u;
     }
     ix->up_pool.clear();
+    if (ix->d_ilv) cudaFree(ix->d_ilv);
     if (ix->d_ext) cudaFree(ix->d_ext);
     if (ix->d_alloc) cudaFree(ix->d_alloc);
     delete ix;
@@ -1103,6 +1146,7 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_SWEEP_MIN: g_sweep_min.store(value); return SVFM_OK;
         case SVFM_TUNE_EXT_BITS: g_ext_bits.store(value); return SVFM_OK;
         case SVFM_TUNE_WORKERS: g_host_workers.store(value); return SVFM_OK;
+        case SVFM_TUNE_ILV: g_ilv.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

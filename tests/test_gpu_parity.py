@@ -17,21 +17,25 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "readme_example.json"
 @pytest.fixture(scope="module", params=["reorder_always", "reorder_never", "defaults", "no_ext_table"])
 def fm(request):
     """Every parity test runs with the batch reordering (sweep search for fixed-length batches, locality sort for the
-    rest) forced on, forced off, at its default thresholds, and without the extended k-mer table (so that long
-    patterns seed from the blob's own kLTS): results must not depend on any of it."""
+    rest) forced on, forced off (and the kernels reading the blob's occ sections in place instead of the interleaved
+    copy), at its default thresholds, and without the extended k-mer table (so that long patterns seed from the blob's
+    own kLTS): results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
     L = _ffi.lib()
     never = 2**64 - 1
-    sort_min, sweep_min, ext_bits = {"reorder_always": (0, 0, 24), "reorder_never": (never, never, 24),
-                                     "defaults": (1 << 17, 1 << 20, 24), "no_ext_table": (1 << 17, 0, 0)}[request.param]
+    sort_min, sweep_min, ext_bits, ilv = {"reorder_always": (0, 0, 24, 1), "reorder_never": (never, never, 24, 0),
+                                          "defaults": (_ffi.SVFM_TUNE_AUTO, 3 << 20, 24, 1),
+                                          "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1)}[request.param]
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, ext_bits) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
     yield fm
-    L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 1 << 17)
-    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, 1 << 20)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, 3 << 20)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, 24)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
