@@ -170,7 +170,7 @@ void svfm_host_free(void* p);
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
  *                      pipeline upload / kernels / download (0 = one chunk; default 8 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
- *                      kept sorted by SA position and moves through the index as streams (default 3 Mi, the measured
+ *                      kept sorted by SA position and moves through the index as streams (default 5 Mi, the measured
  *                      break-even with the plain search kernel on a 1 Gbp index; env SVFM_SWEEP_MIN).
  * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries, derived
  *                      from the blob at load (0 = none; default 24 = 128 MiB for u32 positions; env SVFM_EXT_BITS).

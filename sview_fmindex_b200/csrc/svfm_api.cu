@@ -206,7 +206,7 @@ static uint64_t sort_min_patterns(const svfm_index* ix) {
 }
 static std::atomic<uint64_t> g_sweep_min{[] {
     const char* e = std::getenv("SVFM_SWEEP_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(3u << 20);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(5u << 20);
 }()};
 static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
     const char* e = std::getenv("SVFM_EXT_BITS");
