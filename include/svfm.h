@@ -95,6 +95,9 @@ int svfm_load_device(const uint8_t* d_blob, size_t blob_len, svfm_type t, int de
                      uint64_t err_detail[2]);
 void svfm_free(svfm_index* ix);
 int svfm_index_info(const svfm_index* ix, svfm_info* out);
+/* Device memory held by the handle, in bytes: out[0] the blob copy, out[1] the extended k-mer table, out[2] the
+ * interleaved occ copy, out[3] scratch arenas of the idle sessions / upload staging (grow-only until svfm_free). */
+int svfm_index_memory(svfm_index* ix, uint64_t out[4]);
 /* Host-only part of load: validate + report sizes without touching a device (LoadError paths). */
 int svfm_check_blob(const uint8_t* blob, size_t blob_len, svfm_type t, svfm_info* out, uint64_t err_detail[2]);
 

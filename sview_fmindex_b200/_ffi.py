@@ -61,6 +61,7 @@ EXPORTS = [
     ("svfm_load_device", C.c_int, [_vp, C.c_size_t, SvfmType, C.c_int, C.POINTER(_vp), _u64p]),
     ("svfm_free", None, [_vp]),
     ("svfm_index_info", C.c_int, [_vp, C.POINTER(SvfmInfo)]),
+    ("svfm_index_memory", C.c_int, [_vp, _u64p]),
     ("svfm_check_blob", C.c_int, [_vp, C.c_size_t, SvfmType, C.POINTER(SvfmInfo), _u64p]),
     ("svfm_count_batch", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     ("svfm_locate_batch", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint64, _u64p]),

@@ -18,8 +18,6 @@
 #include <thrust/iterator/reverse_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
-#include <thrust/iterator/reverse_iterator.h>
-
 #include "engine.cuh"
 
 namespace svfm {
@@ -30,10 +28,6 @@ std::atomic<uint64_t> g_launches{0};
 // ---------------------------------------------------------------------------------------------
 // index handle
 // ---------------------------------------------------------------------------------------------
-}  // namespace svfm
-
-namespace svfm {
-
 static int finish_load(svfm_index* ix) {
     // text length is not stored in a header: it equals count_array[S] (count_array.rs:117,125)
     const Layout& L = ix->L;
@@ -91,10 +85,8 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
         blob_len, t, L, err_detail);
     if (rc) return rc;
     SVFM_CUDA(cudaSetDevice(device));
-    // Sparse 32-byte gathers dominate: ask L2 to fetch single sectors instead of 64-byte pairs (ncu, round 1:
-    // with the default granularity half of the DRAM sectors read by the search kernel were never requested).
-    (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    (void)cudaGetLastError();
+    // (cudaLimitMaxL2FetchGranularity = 32 was tried here: on B200 it reads back but L2 still fills 64-byte sector
+    // pairs -- tools/l2gran.cu -- so the library leaves the device limits alone.)
     svfm_index* ix = new svfm_index();
     ix->type = t;
     ix->L = L;
@@ -1015,6 +1007,24 @@ int svfm_index_info(const svfm_index* ix, svfm_info* out) {
     out->off_suffix_array = ix->L.off_suffix_array;
     out->off_rank_checkpoints = ix->L.off_rank_checkpoints;
     out->off_blocks = ix->L.off_blocks;
+    return SVFM_OK;
+}
+
+int svfm_index_memory(svfm_index* ix, uint64_t out[4]) {
+    if (!ix || !out) return SVFM_ERR_BAD_ARG;
+    out[0] = ix->blob_len;
+    out[1] = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
+    out[2] = ix->d_ilv ? ix->L.blocks_len * (uint64_t)ix->ilv_stride : 0;
+    uint64_t scratch = 0;
+    std::lock_guard<std::mutex> g(ix->pool_mu);
+    for (const svfm_session* s : ix->pool)
+        for (const DeviceBuffer* b : {&s->sp, &s->cnt, &s->counts_out, &s->woffs, &s->out_offs, &s->positions, &s->positions_alt,
+                                      &s->cub_temp, &s->keys0, &s->keys1, &s->vals0, &s->vals1, &s->pay0, &s->pay1, &s->items0,
+                                      &s->items1, &s->sweep_hist, &s->sweep_desc, &s->rec_key, &s->rec_key_alt, &s->first,
+                                      &s->heavy_sp, &s->heavy_cnt, &s->heavy_obase, &s->heavy_pat, &s->heavy_offs})
+            scratch += b->cap;
+    for (const svfm_uploader* u : ix->up_pool) scratch += u->pats.cap + u->offs.cap;
+    out[3] = scratch;
     return SVFM_OK;
 }
 

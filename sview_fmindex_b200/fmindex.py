@@ -212,6 +212,12 @@ class FmIndex:
         _raise(_ffi.lib().svfm_index_info(self._h, C.byref(info)))
         return info
 
+    def memory(self) -> dict:
+        """Device bytes held by the handle: the blob copy, the two derived structures, idle scratch."""
+        out = (C.c_uint64 * 4)()
+        _raise(_ffi.lib().svfm_index_memory(self._h, out))
+        return {"blob": int(out[0]), "ext_table": int(out[1]), "interleaved_occ": int(out[2]), "scratch": int(out[3])}
+
     # ---- single pattern: the reference's API -----------------------------------------------------
     def count(self, pattern) -> int:
         p = _as_u8(pattern)

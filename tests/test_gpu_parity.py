@@ -124,11 +124,11 @@ def test_fixed_length_batches_every_type(oracle, fm):
                 continue  # all 30 types for DNA, a spread of them for the wider alphabets
             ora, gpu, table, sc = _pair(oracle, fm, bytes(text), symbols, p, nn, v, 2, 3, with_wildcard=with_wildcard)
             bits = max(1, int(np.ceil(np.log2(sc))))
-            for ln in (1, 3, 6, 7, 11, 64 // bits, 64 // bits + 7, 40):
+            for ln in (1, 2, 3, 4, 5, 6, 7, 11, 64 // bits, 64 // bits + 7, 40):
                 m = 300
                 starts = rng.integers(0, n - ln, size=m)
                 pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
-                pats[::5, rng.integers(0, ln)] = chr_list[0]          # mutate: many become absent
+                pats[::5, int(rng.integers(0, ln))] = chr_list[0]     # mutate: many become absent
                 pats[7::31, ln - 1] = ord("~")                        # wildcard / unmapped byte
                 oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
                 assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc), (p, nn, v, ln)
