@@ -255,7 +255,8 @@ ext_expand_kernel(const DevIndex<P> ix, const P* __restrict__ in, uint64_t n_in,
 // ---- sweep search of a dense fixed-length batch ------------------------------------------------------------------
 // The whole batch moves through the index in SA order.  Every pattern becomes an item
 //   prefix : index of its trailing m symbols in the extended table (0xffffffff: contains a symbol that never occurs)
-//   rest   : the other len-m symbols, `bits` each, the one consumed first in the lowest bits
+//   rest   : the other len-m symbols as ranks among the occurring symbols, `bits` = ceil(log2 s_eff) each, the one
+//            consumed first in the lowest bits
 //   idx    : the caller's pattern index.
 // Items are radix-sorted by prefix, i.e. by the SA interval of their m-symbol suffix; one streaming pass over the
 // table seeds (sp, count).  Then rounds of T backward steps (with_slice.rs:27-31) + a stable radix partition by the
@@ -343,13 +344,13 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
             const uint32_t v = s_lut[byte];
             flags |= v & 0x8000u;
             const uint32_t j = pb.reversed ? f : len - 1 - f;  // j-th symbol from the end of the pattern
+            flags |= v & 0x4000u;  // a symbol that never occurs in the text: count 0, wherever it sits
+            const uint32_t r = (v >> 8) & 0x3fu;
             if (j < m) {
-                flags |= v & 0x4000u;
-                const uint32_t r = (v >> 8) & 0x3fu;
                 if (pb.reversed) { e += r * mult; mult *= syms.s_eff; }  // j ascends: least significant digit first
                 else e = e * syms.s_eff + r;                             // j descends: Horner
             } else {
-                rest |= (R)(v & 0xffu) << (bits * (j - m));
+                rest |= (R)r << (bits * (j - m));
             }
         }
         if (flags & 0x8000u) errbits |= ERRBIT_BAD_SYMBOL;
@@ -462,6 +463,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     using Item = SweepItem<P, R>;
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ P s_count[65];
+    __shared__ uint8_t s_present[64];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_scan[ROUND_WARPS];
     // dynamic: items[ROUND_TILE] | whist[ROUND_WARPS][nbins] | binstart[nbins] | tilebin[nbins] | gbase[nbins] (u64)
@@ -472,6 +474,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     uint32_t* s_tilebin = s_whist + ROUND_WARPS * nbins;
 
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_present[i] = ix.present[i];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     if (PART) {
@@ -559,7 +562,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
             if (cnt[k] != 0) {
                 P ep = (P)(sp[k] + cnt[k]);
                 for (uint32_t t = 0; t < steps && sp[k] < ep; t++)
-                    backward_step<P, NPL, VBITS>(ix, s_count, (uint32_t)((rest[k] >> (shift + bits * t)) & sym_mask), sp[k], ep);
+                    backward_step<P, NPL, VBITS>(ix, s_count, s_present[(uint32_t)((rest[k] >> (shift + bits * t)) & sym_mask)], sp[k], ep);
                 cnt[k] = (P)(ep - sp[k]);
             }
             if (io.heavy_seen && (uint64_t)cnt[k] > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);

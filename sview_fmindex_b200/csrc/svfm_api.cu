@@ -219,19 +219,23 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
     p.bits = (uint32_t)bits_for(S);
     if (p.bits == 0) p.bits = 1;
     if (n > 0xffffffffull) return p;
+    // sweep items carry the symbols beyond the table's m as RANKS among the symbols that occur in the text (a pattern
+    // with any other symbol has count 0 before the search starts), ceil(log2 s_eff) bits each
+    uint32_t rank_bits = (uint32_t)bits_for(ix->symbols_present);
+    if (rank_bits == 0) rank_bits = 1;
     if (!pb.offs && ix->ext_m && n >= g_sweep_min.load() && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
-        pb.fixed_len >= ix->ext_m &&
-        (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits <= 64) {
+        pb.fixed_len >= ix->ext_m && (uint64_t)(pb.fixed_len - ix->ext_m) * rank_bits <= 64) {
         p.sweep = true;
+        p.bits = rank_bits;
         p.m = ix->ext_m;
         p.prefix_bits = bits_for(ix->ext_entries) < 1 ? 1 : bits_for(ix->ext_entries);
         p.rest64 = (uint64_t)(pb.fixed_len - ix->ext_m) * p.bits > 32;
         // steps per round: the partition digit (bits * steps) has at most ROUND_MAX_BINS values; more steps per round
         // save partitions but interleave more symbol classes inside a round
         static const uint32_t t_env = [] { const char* e = std::getenv("SVFM_SWEEP_STEPS"); return e ? (uint32_t)atoi(e) : 0u; }();
-        uint32_t t = t_env ? t_env : 8u / p.bits;
+        uint32_t t = t_env ? t_env : 6u / p.bits;
         while (t > 1 && p.bits * t > 9) t--;
-        p.steps_per_round = t < 1 ? 1 : (t > 3 && !t_env ? 3 : t);
+        p.steps_per_round = t < 1 ? 1 : t;
         return p;
     }
     if (n < sort_min_patterns(ix)) return p;
