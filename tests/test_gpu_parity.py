@@ -241,6 +241,8 @@ def test_load_errors(oracle, fm):
         fm.FmIndex.load(blob[:64], ft)
     ix = fm.FmIndex.load(blob, ft)
     assert ix.count(b"ACG") == 2
+    mem = ix.memory()  # the blob copy byte for byte; derived structures only when enabled
+    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch"}
 
 
 def test_medium_random_batch(oracle, fm):
