@@ -349,6 +349,49 @@ def test_chunked_host_pipeline(oracle, fm):
         L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
 
 
+def test_randomized_configs(oracle, fm):
+    """Seeded fuzz over the whole configuration space: type triple, alphabet size (with / without wildcard), text length
+    around the block boundaries, kLTS k, SA ratio, fixed- and variable-length batches, slice and reversed input,
+    EncodingTable and PassThrough -- always bit-exact against the oracle on the same blob."""
+    rng = np.random.default_rng(20261018)
+    for case in range(24):
+        p, nn, v = ALL_TYPES[int(rng.integers(0, len(ALL_TYPES)))]
+        max_sym = 1 << nn
+        with_wildcard = bool(rng.integers(0, 2))
+        chr_count = int(rng.integers(2, max_sym + 1 - (1 if with_wildcard else 0))) if max_sym > 2 + with_wildcard else 2 - 0
+        chr_count = max(2, min(chr_count, max_sym - (1 if with_wildcard else 0)))
+        chr_list = gen_rand_chr_list(rng, chr_count)
+        n = int(rng.choice([v - 1, v, v + 1, 3 * v, 1000, 4097, 20000]))
+        text = np.frombuffer(bytes(chr_list), dtype=np.uint8)[rng.integers(0, chr_count, size=n)].copy()
+        if with_wildcard and n > 10:
+            text[rng.integers(0, n, size=max(1, n // 97))] = ord("~")
+        k = int(rng.integers(1, 5))
+        r = int(rng.choice([1, 2, 3, 4, 7, 16]))
+        passthrough = bool(rng.integers(0, 4) == 0) and not with_wildcard
+        symbols = [bytes([c]) for c in chr_list]
+        ora, gpu, table, sc = _pair(oracle, fm, bytes(text), symbols, p, nn, v, k, r, passthrough=passthrough,
+                                    with_wildcard=with_wildcard)
+        src = table[text] if passthrough else text
+        # fixed-length batch
+        ln = int(rng.integers(1, min(n, 24) + 1))
+        m = 257
+        starts = rng.integers(0, n - ln + 1, size=m)
+        pats = src[starts[:, None] + np.arange(ln)[None, :]].copy()
+        if ln > 1:
+            pats[::3, int(rng.integers(0, ln))] = src[0]
+        oc, oo, op_, _ = ora.locate_batch(pats, threads=2)
+        assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc), (case, p, nn, v, chr_count, n, k, r, ln)
+        offs, pos = gpu.locate_batch(pats)
+        assert np.array_equal(offs, oo) and np.array_equal(pos.astype(np.uint64), op_.astype(np.uint64)), (case, p, nn, v, n, k, r, ln)
+        assert np.array_equal(gpu.count_batch(pats[:, ::-1], reversed_=True).astype(np.uint64), oc)
+        # variable-length batch, sorted positions
+        var = [bytes(src[s0:s0 + int(rng.integers(1, min(n - s0, 30) + 1))]) for s0 in rng.integers(0, n, size=64)]
+        offs_v, pos_v = gpu.locate_batch(var, sorted_=True)
+        for i, q in enumerate(var):
+            assert np.array_equal(pos_v[int(offs_v[i]):int(offs_v[i + 1])].astype(np.uint64), np.sort(ora.locate(q))), (case, q)
+        gpu.close()
+
+
 def test_concurrent_callers(oracle, fm):
     """`FmIndex` is Send + Sync in the reference (immutable &self queries): concurrent batch calls on ONE handle from
     several host threads must each get their own stream + scratch arena and the right answers."""
