@@ -152,7 +152,7 @@ int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint6
  * launches[] = kernels launched in the phase.  Reading synchronises the session's stream. */
 enum {
     SVFM_PHASE_PRESORT = 0, /* pattern encoding/packing + locality sort of the batch */
-    SVFM_PHASE_SEARCH = 1,  /* backward-search kernels (search_kernel / sweep_step_kernel) */
+    SVFM_PHASE_SEARCH = 1,  /* backward-search kernels (search_kernel / sweep_round_kernel) */
     SVFM_PHASE_SCAN = 2,    /* exclusive prefix sum of the counts -> CSR offsets */
     SVFM_PHASE_LOCATE = 3,  /* LF-walk + sampled-SA lookup kernel */
     SVFM_PHASE_SEGSORT = 4, /* optional per-pattern sort of the positions (SVFM_SORTED) */

@@ -1,5 +1,6 @@
 // search_kernels.cuh -- hand-written CUDA (sm_100a) for the hot path: backward-search count and
-// SA-sampled locate over a batch of patterns.  HBM-bound integer work: no tensor cores, no TMA.
+// SA-sampled locate over a batch of patterns.  HBM-bound integer work: no tensor cores; TMA only as bulk copies that
+// stage pattern bytes in shared memory (pack_sweep_kernel).
 // Citations are relative to the reference's sview-fmindex/src/.
 #pragma once
 #include "device_index.cuh"
