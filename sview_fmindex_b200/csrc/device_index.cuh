@@ -92,31 +92,33 @@ struct Block {
     using W = typename T::W;
     W w[NPL][T::WORDS];
 
-    // 64-bit words: the block is fetched with 16-byte loads (the blocks section is 32-byte aligned on the device,
-    // see svfm_load).  With an odd word count a block starts on an 8-byte boundary every other time: load the
-    // aligned window and shift by one word.  Fewer, wider loads matter because the L1 tag stage handles about one
-    // sector per cycle per SM (ncu, round 1: late backward steps were bound there, not in DRAM).
+    // In-place load from the blob's `blocks` section.  Blocks are only 8-byte aligned there (an odd word count puts every
+    // other block on an odd word), so 64-bit words are fetched one by one; 16-byte window loads + a conditional shift were
+    // measured slower once the sweep search made neighbouring lanes share blocks (round 1: 14.17 -> 13.64 ms of
+    // sweep_round_kernel time per 10^8 patterns).  Even word counts (Block2/4/6<u64>, u128 vectors) load 16 bytes at a time:
+    // the blocks section is shifted onto a 32-byte boundary at load (svfm_load).
     __device__ __forceinline__ void load(const void* blocks, uint64_t q) {
         constexpr int NW = NPL * T::WORDS;
-        if constexpr (sizeof(W) == 8) {
-            const uint64_t wi = q * (uint64_t)NW;
-            constexpr int CH = (NW + 2) / 2;  // chunks of two words covering NW (+1 when misaligned) words
-            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const W*>(blocks) + (wi & ~1ull));
-            unsigned long long raw[2 * CH];
-#pragma unroll
-            for (int c = 0; c < CH; c++) {
-                if (2 * c < NW + (NW & 1)) {  // even NW: exactly NW/2 chunks; odd NW: (NW+1)/2 chunks
-                    const ulonglong2 v = __ldg(p + c);
-                    raw[2 * c] = v.x;
-                    raw[2 * c + 1] = v.y;
-                }
-            }
-            const bool odd = (NW & 1) && (wi & 1ull);
+        if constexpr (sizeof(W) == 8 && (NW & 1)) {
+            const unsigned long long* base = reinterpret_cast<const unsigned long long*>(blocks) + q * (uint64_t)NW;
 #pragma unroll
             for (int i = 0; i < NW; i++) {
-                const W word = (NW & 1) ? (odd ? raw[i + 1] : raw[i]) : raw[i];
+                const W word = __ldg(base + i);
                 if (T::WORDS == 1) w[i][0] = word;
-                else w[i / 2][(i & 1) ? 0 : T::WORDS - 1] = word;  // u128: low half first in memory
+                else w[i / 2][(i & 1) ? 0 : T::WORDS - 1] = word;
+            }
+        } else if constexpr (sizeof(W) == 8) {
+            const ulonglong2* p = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const W*>(blocks) + q * (uint64_t)NW);
+#pragma unroll
+            for (int c = 0; c < NW / 2; c++) {
+                const ulonglong2 v = __ldg(p + c);
+                const W pair[2] = {v.x, v.y};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int i = 2 * c + h;
+                    if (T::WORDS == 1) w[i][0] = pair[h];
+                    else w[i / 2][(i & 1) ? 0 : T::WORDS - 1] = pair[h];  // u128: low half first in memory
+                }
             }
         } else {
             const W* base = reinterpret_cast<const W*>(blocks) + q * (uint64_t)NW;

@@ -75,6 +75,8 @@ struct svfm_session {
 
 namespace svfm {
 
+constexpr int MAX_DYNAMIC_SMEM = 200 * 1024;  // opt-in dynamic shared memory per CTA (B200: up to 227 KB)
+
 template <class P>
 static DevIndex<P> make_dev_index(const svfm_index* ix) {
     const Layout& L = ix->L;
@@ -321,7 +323,10 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
         if (part) SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
         const size_t smem = part ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 : 0;
         auto launch = [&](auto kernel) -> int {
-            if (smem > 48 * 1024) SVFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // always the same value: concurrent sessions launch this kernel with different sizes, and the attribute is
+            // per function, not per launch
+            SVFM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYNAMIC_SMEM));
+            if (smem > (size_t)MAX_DYNAMIC_SMEM) return SVFM_ERR_TOO_LARGE;
             int per_sm = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ROUND_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
             uint64_t grid = n_tiles < (uint64_t)sms * per_sm ? n_tiles : (uint64_t)sms * per_sm;

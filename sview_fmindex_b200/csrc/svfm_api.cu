@@ -375,7 +375,9 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     syms.s_eff = ix->symbols_present;
     std::memcpy(syms.sym_rank, ix->sym_rank, 64);
     const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) + (size_t)rounds * nb_max * 4;
-    SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // always the same value (concurrent sessions pack batches of different pattern lengths; the attribute is per function)
+    SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYNAMIC_SMEM));
+    if (smem > (size_t)MAX_DYNAMIC_SMEM) return SVFM_ERR_TOO_LARGE;
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;

@@ -406,8 +406,8 @@ def test_concurrent_callers(oracle, fm):
     ora = po.OracleFmIndex.load(blob, t)
     gpu = fm.FmIndex.load(blob, fm.IndexType(32, 3, 64, True))
     jobs = []
-    for j in range(6):
-        ln = 6 + 3 * j
+    for j in range(8):
+        ln = 5 + 3 * j
         starts = rng.integers(0, n - ln, size=40_000)
         pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
         pats[::9, 1] = ord("C")
@@ -417,7 +417,7 @@ def test_concurrent_callers(oracle, fm):
     def worker(j):
         try:
             pats, (oc, oo, op_, _) = jobs[j]
-            for _ in range(3):
+            for _ in range(6):
                 assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc)
                 offs, pos = gpu.locate_batch(pats)
                 assert np.array_equal(offs, oo) and np.array_equal(pos, op_)
