@@ -120,8 +120,8 @@ int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, 
 int svfm_locate_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n,
                       uint32_t fixed_len, uint32_t flags, uint64_t* out_offs, void* positions,
                       uint64_t capacity, uint64_t* total);
-/* Same, positions allocated by the library in pinned host memory (like the Vec<P> `locate` returns);
- * release with svfm_free_positions. */
+/* Same, positions allocated by the library (like the Vec<P> `locate` returns; pinned host memory for results of
+ * 1 MiB and more, plain memory below); release with svfm_free_positions only. */
 int svfm_locate_batch_alloc(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n,
                             uint32_t fixed_len, uint32_t flags, uint64_t* out_offs, void** positions,
                             uint64_t* total);

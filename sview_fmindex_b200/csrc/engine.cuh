@@ -56,7 +56,7 @@ struct svfm_uploader {
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
     svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records

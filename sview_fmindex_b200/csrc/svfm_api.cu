@@ -581,6 +581,33 @@ static double now_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+// Result buffers handed to the caller (svfm_locate_batch_alloc): pinned memory for large results (asynchronous
+// device-to-host copies), plain aligned memory below 1 MiB -- cudaHostAlloc/cudaFreeHost cost tens of microseconds,
+// which dominates a single-pattern `locate`.  A 64-byte header in front of the data records which one it is.
+struct ResultHeader { uint64_t magic, pinned; uint8_t pad[48]; };
+static_assert(sizeof(ResultHeader) == 64, "result header");
+constexpr uint64_t RESULT_MAGIC = 0x5356464d52534c54ull;  // "SVFMRSLT"
+static void* result_alloc(uint64_t bytes) {
+    void* raw = nullptr;
+    const bool pinned = bytes >= (1u << 20);
+    if (pinned) {
+        if (cudaHostAlloc(&raw, bytes + sizeof(ResultHeader), cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    } else if (posix_memalign(&raw, 64, bytes + sizeof(ResultHeader)) != 0) {
+        return nullptr;
+    }
+    ResultHeader* h = static_cast<ResultHeader*>(raw);
+    h->magic = RESULT_MAGIC;
+    h->pinned = pinned ? 1 : 0;
+    return h + 1;
+}
+static void result_free(void* p) {
+    if (!p) return;
+    ResultHeader* h = static_cast<ResultHeader*>(p) - 1;
+    if (h->magic != RESULT_MAGIC) return;  // not ours: leave it alone rather than corrupt the heap
+    h->magic = 0;
+    if (h->pinned) cudaFreeHost(h); else std::free(h);
+}
+
 __global__ void add_base_kernel(uint64_t* __restrict__ v, uint64_t n, uint64_t base) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] += base;
 }
@@ -796,10 +823,45 @@ static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, Fn&& per_chunk,
     return first_err.load();
 }
 
+// Single-chunk batches (every single-pattern call among them) skip the upload stream and the worker threads: the
+// copies go on the leased session's own stream.
+static int upload_direct(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len, uint32_t flags,
+                         PatternBatch& pb) {
+    int rc;
+    pb.n = n;
+    pb.fixed_len = fixed_len;
+    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.offs = nullptr;
+    const uint64_t bytes = offs ? offs[n] - offs[0] : n * (uint64_t)fixed_len;
+    if ((rc = s->pats.reserve(bytes + 256))) return rc;
+    SVFM_CUDA(cudaMemcpyAsync(s->pats.ptr, pats + (offs ? offs[0] : 0), bytes, cudaMemcpyHostToDevice, s->stream));
+    pb.pats = (const uint8_t*)s->pats.ptr - (offs ? offs[0] : 0);  // offsets stay absolute
+    if (offs) {
+        if ((rc = s->offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
+        SVFM_CUDA(cudaMemcpyAsync(s->offs.ptr, offs, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        pb.offs = (const uint64_t*)s->offs.ptr;
+    }
+    return SVFM_OK;
+}
+
 static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
                       uint32_t flags, void* counts_out) {
     const uint64_t P = ix->type.pos_bits / 8;
     const ChunkPlan cp = plan_chunks(n);
+    if (cp.chunks == 1) {
+        SessionLease lease(ix);
+        int r = lease.acquire();
+        if (r) return r;
+        svfm_session* s = lease.s;
+        PatternBatch pb;
+        if ((r = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return r;
+        if ((r = s->counts_out.reserve(n * P))) return r;
+        if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
+        SVFM_CUDA(cudaMemcpyAsync(counts_out, s->counts_out.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        return err_from_bits((int)(s->h_pinned[1] & 0xffffffffu));
+    }
     UploaderLease up(ix);
     int rc = up.acquire();
     if (rc) return rc;
@@ -839,6 +901,32 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
     if (n == 0) return SVFM_OK;
     const uint64_t P = ix->type.pos_bits / 8;
     const ChunkPlan cp = plan_chunks(n);
+    if (cp.chunks == 1) {  // no upload stream, no worker threads
+        SessionLease lease(ix);
+        if ((rc = lease.acquire())) return rc;
+        svfm_session* s = lease.s;
+        PatternBatch pb;
+        if ((rc = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return rc;
+        if ((rc = s->out_offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
+        void* d_positions = nullptr;
+        uint64_t total = 0;
+        if ((rc = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return rc;
+        *total_out = total;
+        SVFM_CUDA(cudaMemcpyAsync(out_offs, s->out_offs.ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        void* dst = positions;
+        if (alloc_out && total) {
+            if (!(dst = result_alloc(total * P))) { cudaStreamSynchronize(s->stream); return SVFM_ERR_NOMEM; }
+        }
+        const bool fits = alloc_out || total <= capacity;
+        cudaError_t e = (total && fits) ? cudaMemcpyAsync(dst, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            if (alloc_out && total) result_free(dst);
+            SVFM_CUDA(e);
+        }
+        if (alloc_out) *alloc_out = total ? dst : nullptr;
+        return fits ? SVFM_OK : SVFM_ERR_CAPACITY;
+    }
     // chunk totals are published in completion order; a chunk's output base is the sum of all earlier totals
     std::mutex mu;
     std::condition_variable cv;
@@ -890,9 +978,8 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         SVFM_CUDA(cudaMemcpyAsync(out_offs + a, s->out_offs.ptr, n_offs * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
         if (total) {
             if (alloc_out) {
-                void* buf = nullptr;
-                cudaError_t e = cudaHostAlloc(&buf, total * P, cudaHostAllocDefault);
-                if (e != cudaSuccess) { cudaStreamSynchronize(s->stream); g_last_error = cudaGetErrorString(e); return SVFM_ERR_NOMEM; }
+                void* buf = result_alloc(total * P);
+                if (!buf) { cudaStreamSynchronize(s->stream); g_last_error = "result allocation failed"; return SVFM_ERR_NOMEM; }
                 chunk_bufs[c] = buf;
                 SVFM_CUDA(cudaMemcpyAsync(buf, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
             } else if (base + total <= capacity) {
@@ -919,7 +1006,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
                 dst = chunk_bufs[0];
                 chunk_bufs[0] = nullptr;
             } else {
-                if (cudaHostAlloc(&dst, total * P, cudaHostAllocDefault) != cudaSuccess) { rc = SVFM_ERR_NOMEM; dst = nullptr; }
+                if (!(dst = result_alloc(total * P))) rc = SVFM_ERR_NOMEM;
                 uint64_t at = 0;
                 for (uint64_t c = 0; dst && c < cp.chunks; c++) {
                     if (totals[c]) std::memcpy((uint8_t*)dst + at * P, chunk_bufs[c], totals[c] * P);
@@ -928,7 +1015,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
             }
             *alloc_out = dst;
         }
-        for (void* b : chunk_bufs) if (b) cudaFreeHost(b);
+        for (void* b : chunk_bufs) result_free(b);
     }
     if (rc) return rc;
     if (overflow.load() || (!alloc_out && total > capacity)) return SVFM_ERR_CAPACITY;
@@ -1057,7 +1144,7 @@ int svfm_locate_batch_alloc(svfm_index* ix, const uint8_t* pats, const uint64_t*
 }
 
 void svfm_free_positions(void* positions) {
-    if (positions) cudaFreeHost(positions);
+    result_free(positions);
 }
 
 int svfm_count(svfm_index* ix, const uint8_t* pattern, uint64_t len, uint32_t flags, uint64_t* count) {
