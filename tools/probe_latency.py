@@ -5,15 +5,18 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from oracle import pyoracle as po  # noqa: E402  (only to build a small blob on the host)
-from sview_fmindex_b200 import FmIndex, IndexType  # noqa: E402
+from sview_fmindex_b200 import EncodingTable, FmIndex, FmIndexBuilder, IndexType, aligned_empty  # noqa: E402
 
 rng = np.random.default_rng(1)
 n = 2_000_000
 text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)]
-table, sc = po.encoding_table([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
-blob = po.build_blob(po.IndexType(32, 3, 64, True), text, sc, table, 3, 2)
-ix = FmIndex.load(blob, IndexType(32, 3, 64, True))
+enc = EncodingTable.from_symbols([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"])
+it = IndexType(32, 3, 64, True)
+b = FmIndexBuilder(n, enc.symbol_count(), enc, it)
+b.kmer_size, b.sampling_ratio = 3, 2
+blob = aligned_empty(b.blob_size())
+b.build(text, blob)
+ix = FmIndex.load(blob, it)
 pats = [bytes(text[s:s + 20]) for s in rng.integers(0, n - 20, size=2000)]
 for p in pats[:50]:
     ix.count(p); ix.locate(p)
