@@ -173,10 +173,13 @@ void svfm_host_free(void* p);
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
  *                      pipeline upload / kernels / download (0 = one chunk; default 8 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
- *                      kept sorted by SA position and moves through the index as streams (default 5 Mi, the measured
- *                      break-even with the plain search kernel on a 1 Gbp index; env SVFM_SWEEP_MIN).
- * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries, derived
- *                      from the blob at load (0 = none; default 24 = 128 MiB for u32 positions; env SVFM_EXT_BITS).
+ *                      kept sorted by SA position and moves through the index as streams (default SVFM_TUNE_AUTO = the
+ *                      measured break-even with the plain search kernel on a 1 Gbp index: 5 Mi patterns with a 2^24-entry
+ *                      extended table, 10 Mi with a 2^28-entry one; env SVFM_SWEEP_MIN).
+ * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries (and at most
+ *                      text_len / 2), derived from the blob at load (0 = none; default SVFM_TUNE_AUTO = 28, i.e. 2 GiB
+ *                      for u32 positions, when that is under 1/16 of the free device memory, else 24 = 128 MiB; env
+ *                      SVFM_EXT_BITS).
  * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS).
  * SVFM_TUNE_ILV      : indexes loaded from now on also get an interleaved copy of the occ data -- block q and checkpoint
  *                      row q in one aligned 32/64/128-byte slot -- which the gather-bound kernels read instead of the two

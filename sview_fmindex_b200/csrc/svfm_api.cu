@@ -198,12 +198,29 @@ static uint64_t sort_min_patterns(const svfm_index* ix) {
 }
 static std::atomic<uint64_t> g_sweep_min{[] {
     const char* e = std::getenv("SVFM_SWEEP_MIN");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(5u << 20);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
+// AUTO: the measured break-even with the plain search kernel on a 1 Gbp index -- about 5.5 M patterns with a 2^24-entry
+// extended table (8 steps left of a 20-mer), about 10 M with a 2^28-entry one (6 steps left).
+static uint64_t sweep_min_patterns(const svfm_index* ix) {
+    const uint64_t v = g_sweep_min.load();
+    if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
+    return ix->ext_entries >= (1ull << 26) ? (uint64_t)(10u << 20) : (uint64_t)(5u << 20);
+}
 static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
     const char* e = std::getenv("SVFM_EXT_BITS");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)24;
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
+// AUTO: 2^28 entries (2 GiB with u32 positions: 14 DNA symbols per lookup) when that is at most 1/16 of the device
+// memory still free after the blob upload -- HBM capacity is what a B200 has plenty of -- else 2^24 (128 MiB).
+static uint64_t ext_bits_for(const svfm_index* ix) {
+    const uint64_t v = g_ext_bits.load();
+    if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 24; }
+    const uint64_t big = (1ull << 28) * 2 * (ix->type.pos_bits / 8);
+    return big <= free_b / 16 ? 28 : 24;
+}
 static std::atomic<uint64_t> g_ilv{[] {  // build the interleaved occ copy at load
     const char* e = std::getenv("SVFM_ILV");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
@@ -223,7 +240,7 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
     // with any other symbol has count 0 before the search starts), ceil(log2 s_eff) bits each
     uint32_t rank_bits = (uint32_t)bits_for(ix->symbols_present);
     if (rank_bits == 0) rank_bits = 1;
-    if (!pb.offs && ix->ext_m && n >= g_sweep_min.load() && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
+    if (!pb.offs && ix->ext_m && n >= sweep_min_patterns(ix) && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
         pb.fixed_len >= ix->ext_m && (uint64_t)(pb.fixed_len - ix->ext_m) * rank_bits <= 64) {
         p.sweep = true;
         p.bits = rank_bits;
@@ -447,7 +464,7 @@ static int build_ilv_table(svfm_index* ix) {
 }
 static int build_ext_table(svfm_index* ix) {
     const TypeOps* ops = type_ops(ix->type);
-    return ops ? ops->build_ext(ix->type.planes, ix, g_ext_bits.load()) : SVFM_ERR_BAD_TYPE;
+    return ops ? ops->build_ext(ix->type.planes, ix, ext_bits_for(ix)) : SVFM_ERR_BAD_TYPE;
 }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
                            const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {

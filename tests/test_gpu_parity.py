@@ -25,7 +25,7 @@ def fm(request):
     L = _ffi.lib()
     never = 2**64 - 1
     sort_min, sweep_min, ext_bits, ilv = {"reorder_always": (0, 0, 24, 1), "reorder_never": (never, never, 24, 0),
-                                          "defaults": (_ffi.SVFM_TUNE_AUTO, 5 << 20, 24, 1),
+                                          "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1),
                                           "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1)}[request.param]
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
@@ -33,8 +33,8 @@ def fm(request):
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
-    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, 5 << 20)
-    L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, 24)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, _ffi.SVFM_TUNE_AUTO)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
 
 
