@@ -35,6 +35,23 @@ def test_library_exports_every_declared_symbol(fm):
     assert b"sm_100a" in _ffi.lib().svfm_version()
 
 
+def test_python_constants_match_the_header():
+    """Every enumerator / macro of include/svfm.h that the ctypes layer mirrors has the header's value."""
+    from sview_fmindex_b200 import _ffi
+    hdr = open(os.path.join(ROOT, "include", "svfm.h")).read()
+    consts = {k: int(v, 0) for k, v in re.findall(r"\b(SVFM_[A-Z0-9_]+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", hdr)}
+    consts.update({k: int(v.rstrip("ulUL"), 0) for k, v in re.findall(r"#define\s+(SVFM_[A-Z0-9_]+)\s+(0x[0-9a-fA-F]+[ulUL]*|\d+[ulUL]*)", hdr)})
+    assert len(consts) > 25
+    mirrored = {k: v for k, v in vars(_ffi).items() if k.startswith("SVFM_") and isinstance(v, int)}
+    assert mirrored
+    for k, v in mirrored.items():
+        assert k in consts, f"{k} is not in include/svfm.h"
+        assert consts[k] == v, (k, consts[k], v)
+    for k in consts:
+        if k.startswith(("SVFM_ERR_", "SVFM_TUNE_")) or k in ("SVFM_OK", "SVFM_REVERSED", "SVFM_SORTED"):
+            assert k in mirrored, f"{k} is missing from sview_fmindex_b200/_ffi.py"
+
+
 def test_product_does_not_reference_the_oracle():
     """The oracle is test infrastructure: nothing under the package may import, link or load it."""
     pkg = os.path.join(ROOT, "sview_fmindex_b200")
