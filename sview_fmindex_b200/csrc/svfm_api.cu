@@ -380,11 +380,15 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
     uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
     size_t t1 = 0;
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
+    // Only the top 24 bits of the table index are sorted (three radix passes): items that differ in the lower bits only
+    // sit in neighbouring table entries and SA rows (a 2^28-entry DNA table: 16 entries = ~60 rows, one occ block), so
+    // leaving them unordered costs no locality, and correctness never depends on the order.
+    const int sort_begin = plan.prefix_bits > 24 ? plan.prefix_bits - 24 : 0;
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, sort_begin, plan.prefix_bits, s->stream));
     if ((rc = s->cub_temp.reserve(t1))) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits + 7) / 8);
+    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits - sort_begin + 7) / 8);
     SVFM_CUDA(cudaMemsetAsync(hist, 0, ((uint64_t)rounds * nb_max + rounds + 64) * 4, s->stream));
     const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
     DevSyms syms;
@@ -402,7 +406,7 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, plan.m, prefix.Current(), pay.Current(),
                                                                         digit_bits, rounds, hist, s->d_err);
     SVFM_CUDA(cudaGetLastError());
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, 0, plan.prefix_bits, s->stream));
+    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, sort_begin, plan.prefix_bits, s->stream));
     out->prefix = prefix.Current();
     out->pay = pay.Current();
     out->hist = hist;
