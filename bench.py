@@ -436,7 +436,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": a_bytes / n_launch,
                 "note": "algorithmic bytes = SURVEY.md 8d per-pattern figure (every rank query counted as a private checkpoint word + "
                         "block, 17 steps from the blob's k=3 table) x patterns, spread evenly over the launches of one batch; "
-                        "the engine resolves 12 symbols with one extended-table lookup and keeps the batch in SA order so that "
+                        "the engine resolves the last 12-14 symbols with one extended-table lookup and keeps the batch in SA order so that "
                         "patterns share index sectors, hence frac > 1; `traffic` (ncu dram bytes per launch) / kernel_ms_per_launch "
                         "is the HBM throughput the kernel really sustains"}
     if traffic:
