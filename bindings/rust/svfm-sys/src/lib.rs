@@ -82,6 +82,8 @@ extern "C" {
     pub fn svfm_locate_batch_device(s: *mut svfm_session, d_pats: *const u8, d_offs: *const u64, n: u64, fixed_len: u32,
                                     flags: u32, d_out_offs: *mut u64, d_positions: *mut *mut c_void,
                                     total: *mut u64) -> c_int;
+    pub fn svfm_session_set_timing(s: *mut svfm_session, enabled: c_int) -> c_int;
+    pub fn svfm_session_get_timing(s: *mut svfm_session, ms: *mut f64, launches: *mut u64, reset: c_int) -> c_int; // [SVFM_PHASE_MAX = 8]
     pub fn svfm_host_alloc(bytes: usize) -> *mut c_void;
     pub fn svfm_host_free(p: *mut c_void);
     pub fn svfm_set_tuning(key: c_int, value: u64) -> c_int;

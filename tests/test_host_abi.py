@@ -52,6 +52,19 @@ def test_python_constants_match_the_header():
             assert k in mirrored, f"{k} is missing from sview_fmindex_b200/_ffi.py"
 
 
+def test_rust_sys_source_declares_the_whole_header():
+    """bindings/rust/svfm-sys is source only (no Rust toolchain in this image): at least keep its `extern "C"` block in
+    step with include/svfm.h, function by function."""
+    hdr = open(os.path.join(ROOT, "include", "svfm.h")).read()
+    declared = set(re.findall(r"\b(svfm_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "bindings", "rust", "svfm-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (svfm_[a-z0-9_]+)\s*\(", rs))
+    assert declared == bound, (declared - bound, bound - declared)
+    for k, v in re.findall(r"\b(SVFM_TUNE_[A-Z_]+)\s*=\s*(\d+)\b", hdr):
+        if k != "SVFM_TUNE_AUTO":  # a #define (u64 sentinel), not an enumerator
+            assert re.search(rf"pub const {k}: c_int = {v};", rs), k
+
+
 def test_product_does_not_reference_the_oracle():
     """The oracle is test infrastructure: nothing under the package may import, link or load it."""
     pkg = os.path.join(ROOT, "sview_fmindex_b200")
