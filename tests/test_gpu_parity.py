@@ -349,6 +349,34 @@ def test_chunked_host_pipeline(oracle, fm):
         L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
 
 
+def test_heavy_patterns_in_fixed_length_batches(oracle, fm):
+    """Patterns with thousands of SA rows (more than HEAVY_ROWS = 1024: the row-parallel locate kernel) inside
+    fixed-length batches, i.e. on the sweep search when it is forced on, mixed with single-hit and absent patterns."""
+    rng = np.random.default_rng(31)
+    text = np.concatenate([np.full(6000, ord("A"), dtype=np.uint8),
+                           np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=30_000)],
+                           np.frombuffer(b"CG" * 2500, dtype=np.uint8)])
+    n = len(text)
+    for (p, nn, v, k, r) in ((32, 3, 64, 3, 2), (64, 2, 128, 2, 4), (32, 2, 32, 1, 1)):
+        symbols = [b"Aa", b"Cc", b"Gg", b"Tt"] + ([b"Nn"] if nn > 2 else [])
+        ora, gpu, _, _ = _pair(oracle, fm, bytes(text), symbols, p, nn, v, k, r)
+        for ln in (2, 6, 9, 17):
+            starts = rng.integers(0, n - ln, size=400)
+            pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
+            pats[::4] = ord("A")                                  # thousands of rows each
+            pats[1::8] = np.frombuffer((b"CG" * ln)[:ln], dtype=np.uint8)
+            pats[2::16, ln - 1] = ord("T")
+            oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
+            assert int(oc.max()) > 1024
+            assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc), (p, nn, v, ln)
+            offs, pos = gpu.locate_batch(pats)
+            assert np.array_equal(offs, oo) and np.array_equal(pos.astype(np.uint64), op_.astype(np.uint64)), (p, nn, v, ln)
+            offs_s, pos_s = gpu.locate_batch(pats[:60], sorted_=True)
+            for i in range(60):
+                assert np.array_equal(pos_s[int(offs_s[i]):int(offs_s[i + 1])].astype(np.uint64), np.sort(ora.locate(bytes(pats[i]))))
+        gpu.close()
+
+
 def test_randomized_configs(oracle, fm):
     """Seeded fuzz over the whole configuration space: type triple, alphabet size (with / without wildcard), text length
     around the block boundaries, kLTS k, SA ratio, fixed- and variable-length batches, slice and reversed input,
