@@ -11,6 +11,7 @@ pub const SVFM_ERR_CAPACITY: c_int = 25;
 pub const SVFM_ERR_CUDA: c_int = 30;
 pub const SVFM_REVERSED: u32 = 1;
 pub const SVFM_SORTED: u32 = 2;
+pub const SVFM_OFFS32: u32 = 4;
 // svfm_set_tuning keys (results never depend on them)
 pub const SVFM_TUNE_SORT_MIN: c_int = 0;
 pub const SVFM_TUNE_CHUNK: c_int = 1;
@@ -18,6 +19,7 @@ pub const SVFM_TUNE_SWEEP_MIN: c_int = 2;
 pub const SVFM_TUNE_EXT_BITS: c_int = 3;
 pub const SVFM_TUNE_WORKERS: c_int = 4;
 pub const SVFM_TUNE_ILV: c_int = 5;
+pub const SVFM_TUNE_BUCKET_SORTBACK: c_int = 6;
 pub const SVFM_TUNE_AUTO: u64 = 0xffff_ffff_ffff_fffe;
 
 #[repr(C)]
@@ -80,8 +82,8 @@ extern "C" {
     pub fn svfm_count_batch_device(s: *mut svfm_session, d_pats: *const u8, d_offs: *const u64, n: u64, fixed_len: u32,
                                    flags: u32, d_counts_out: *mut c_void) -> c_int;
     pub fn svfm_locate_batch_device(s: *mut svfm_session, d_pats: *const u8, d_offs: *const u64, n: u64, fixed_len: u32,
-                                    flags: u32, d_out_offs: *mut u64, d_positions: *mut *mut c_void,
-                                    total: *mut u64) -> c_int;
+                                    flags: u32, d_out_offs: *mut c_void /* u64[n+1]; u32[n+1] with SVFM_OFFS32 */,
+                                    d_positions: *mut *mut c_void, total: *mut u64) -> c_int;
     pub fn svfm_session_set_timing(s: *mut svfm_session, enabled: c_int) -> c_int;
     pub fn svfm_session_get_timing(s: *mut svfm_session, ms: *mut f64, launches: *mut u64, reset: c_int) -> c_int; // [SVFM_PHASE_MAX = 8]
     pub fn svfm_host_alloc(bytes: usize) -> *mut c_void;

@@ -76,8 +76,10 @@ typedef struct svfm_session svfm_session; /* one CUDA stream + scratch arena; on
 enum {
     SVFM_REVERSED = 1, /* patterns are stored back-to-front: count_rev_iter / locate_rev_iter
                           (locate/with_rev_iter.rs:5-38, count_array.rs:235-274) */
-    SVFM_SORTED = 2    /* locate: ascending positions per pattern.  Default is the reference's SA-row
+    SVFM_SORTED = 2,   /* locate: ascending positions per pattern.  Default is the reference's SA-row
                           order (locate/mod.rs:19; "The locations may not be in order", README.md:77) */
+    SVFM_OFFS32 = 4    /* locate: out_offs is uint32_t[n+1] instead of uint64_t[n+1] (half the bytes of a typical
+                          result on the way back to the host); SVFM_ERR_TOO_LARGE when *total >= 2^32 */
 };
 
 /* ---- load ---------------------------------------------------------------------------------
@@ -144,7 +146,7 @@ void* svfm_session_stream(svfm_session* s); /* cudaStream_t */
 int svfm_count_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
                             uint32_t fixed_len, uint32_t flags, void* d_counts_out);
 int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
-                             uint32_t fixed_len, uint32_t flags, uint64_t* d_out_offs,
+                             uint32_t fixed_len, uint32_t flags, void* d_out_offs /* u64[n+1]; u32[n+1] with SVFM_OFFS32 */,
                              void** d_positions, uint64_t* total);
 
 /* ---- per-phase device timing of a session (CUDA events on the session's stream) --------------------
@@ -183,9 +185,13 @@ void svfm_host_free(void* p);
  * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS).
  * SVFM_TUNE_ILV      : indexes loaded from now on also get an interleaved copy of the occ data -- block q and checkpoint
  *                      row q in one aligned 32/64/128-byte slot -- which the gather-bound kernels read instead of the two
- *                      blob sections (1 = build, the default; 0 = search the blob in place only; env SVFM_ILV). */
+ *                      blob sections (1 = build, the default; 0 = search the blob in place only; env SVFM_ILV).
+ * SVFM_TUNE_BUCKET_SORTBACK : how a reordered batch gets back into the caller's order.  1 (default): locate writes its
+ *                      records straight into buckets of 8192 pattern indices and one kernel finishes every bucket in shared
+ *                      memory; `count` groups by the top index bits and scatters.  0: radix sorts by pattern index
+ *                      (env SVFM_BUCKET_SORTBACK). */
 enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
-       SVFM_TUNE_ILV = 5 };
+       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6 };
 #define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */

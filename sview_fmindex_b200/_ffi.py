@@ -34,9 +34,11 @@ SVFM_TUNE_SWEEP_MIN = 2
 SVFM_TUNE_EXT_BITS = 3
 SVFM_TUNE_WORKERS = 4
 SVFM_TUNE_ILV = 5
+SVFM_TUNE_BUCKET_SORTBACK = 6
 SVFM_TUNE_AUTO = 0xFFFFFFFFFFFFFFFE
 SVFM_REVERSED = 1
 SVFM_SORTED = 2
+SVFM_OFFS32 = 4
 
 ERROR_NAMES = {v: k for k, v in list(globals().items()) if k.startswith("SVFM_ERR_")}
 

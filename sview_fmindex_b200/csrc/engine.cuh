@@ -56,12 +56,14 @@ struct svfm_uploader {
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, offs64, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
     svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
-    svfm::DeviceBuffer rec_key, rec_key_alt, first;          // sort-back of (pattern index -> position) records
+    svfm::DeviceBuffer rec_key, rec_key_alt, first;          // radix sort-back of (pattern index -> position) records (SVFM_SORTED)
+    svfm::DeviceBuffer sb_hist, sb_base, sb_cursor, sb_recs; // bucketed sort-back
     svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
-    unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length
+    unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length,
+                                                             // [2] SA rows of the batch (bucketed sort-back)
     int* d_err = nullptr;
     uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
     // per-phase timing (svfm_session_set_timing)
@@ -194,7 +196,7 @@ static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
 // One launch of the search kernel: keys/idx (or NULL) in, sp/cnt out.
 template <class P, int NPL, int VBITS>
 static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                      void* d_sp_work, void* d_cnt_work) {
+                      void* d_sp_work, void* d_cnt_work, const SbOut& sb) {
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
     const bool ilv = dix.ilv != nullptr;
     const int grid = ilv ? resident_grid(search_kernel<P, NPL, VBITS, true>, pb.n, SEARCH_THREADS, s->ix->device)
@@ -207,6 +209,7 @@ static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* k
     io.cnt_out = (P*)d_cnt_work;
     io.heavy_seen = s->d_counters;
     io.err = s->d_err;
+    io.sb = sb;
     PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
     if (ilv) search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
     else search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
@@ -257,6 +260,7 @@ static int run_build_ext(svfm_index* ix, uint64_t ext_bits) {
 
 // Output of the type-independent front of the sweep search (svfm_api.cu): items packed and radix-sorted by table index,
 // digit histograms of every round followed by one zeroed tile counter per round.
+constexpr int SWEEP_INDEX_BITS = 6;  // PART_INDEX: the last round of `count` groups its items by the top 6 bits of the pattern index
 struct SweepPre {
     const uint32_t* prefix;
     const void* pay;   // SweepPay<R>[n]
@@ -269,9 +273,13 @@ extern template int run_sweep_presort<uint64_t>(svfm_session*, const PatternBatc
 
 // Sweep search (search_kernels.cuh): pack -> radix sort by table index -> rounds of [seed/resume + T backward steps +
 // stable radix partition by the consumed symbols], each round ONE kernel.  Leaves sp/cnt/idx of every item in work order.
+// final_mode: what the LAST round does with its items -- PART_NONE: written in place; PART_SYMBOLS (locate): partitioned
+// once more, so that the LF walks and SA reads run in SA order; PART_INDEX (count): grouped by the top bits of the
+// caller's pattern index, ready for scatter_counts_kernel.  sb (sb.hist nullable): the last round also reserves the record
+// slots of the bucketed sort-back.
 template <class P, int NPL, int VBITS, class R>
-static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
-                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {
+static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,
+                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {
     const svfm_index* ix = s->ix;
     const DevIndex<P> dix = make_dev_index<P>(ix);
     const uint64_t n = pb.n;
@@ -284,7 +292,7 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
     int rc;
     if ((rc = s->vals0.reserve(n * 4)) || (rc = s->sweep_desc.reserve(n_tiles * nb_max * 4))) return rc;
-    const bool partitions = rounds > 1 || final_sort;
+    const bool partitions = rounds > 1;
     if (partitions && ((rc = s->items0.reserve(n * sizeof(Item))) || (rc = s->items1.reserve(n * sizeof(Item))))) return rc;
     Item* items[2] = {(Item*)s->items0.ptr, (Item*)s->items1.ptr};
     SweepPre pre{};
@@ -293,6 +301,7 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     const Pay* pay = (const Pay*)pre.pay;
     uint32_t* hist = pre.hist;
     uint32_t* tile_counters = hist + (uint64_t)rounds * nb_max;  // one per round
+    uint32_t* bin_cursor = tile_counters + rounds;               // SWEEP_INDEX_BINS counters (PART_INDEX), zeroed with the rest
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
@@ -301,10 +310,11 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
         const uint32_t first = r * T;
         const uint32_t steps = remaining - first < T ? remaining - first : T;
         const bool last = r + 1 == rounds;
-        const bool part = (!last || final_sort) && steps > 0;
+        int part = PART_SYMBOLS;
+        if (last) part = final_mode == PART_INDEX ? PART_INDEX : (final_mode == PART_SYMBOLS && steps > 0 ? PART_SYMBOLS : PART_NONE);
         // the last partition digit may be narrower than digit_bits: the histogram was taken on digit_bits bits, whose
         // upper bits are then zero, so the wide digit sorts identically
-        const uint32_t nbins = nb_max;
+        uint32_t nbins = nb_max;
         SweepRoundIO<P, R> io{};
         if (r == 0) { io.prefix = prefix; io.pay = pay; }
         else io.items_in = items[cur];
@@ -313,15 +323,29 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
             io.cnt_out = (P*)d_cnt_work;
             io.idx_out = idx_work;
             io.heavy_seen = s->d_counters;
+            io.sb = sb;
         } else {
             io.items_out = items[r == 0 ? 0 : cur ^ 1];
         }
         io.hist = hist + (uint64_t)r * nb_max;
         io.desc = (uint32_t*)s->sweep_desc.ptr;
         io.tile_counter = tile_counters + r;
+        if (part == PART_INDEX) {
+            const int nbits = bits_for(n);
+            io.idx_shift = nbits > SWEEP_INDEX_BITS ? (uint32_t)(nbits - SWEEP_INDEX_BITS) : 0u;
+            io.bin_cursor = bin_cursor;
+            nbins = 1u << SWEEP_INDEX_BITS;
+        }
+        static const bool arrival_order = [] { const char* e = std::getenv("SVFM_ROUND_ATOMIC"); return e ? atoi(e) != 0 : false; }();
         PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-        if (part) SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
-        const size_t smem = part ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 : 0;
+        if (part == PART_SYMBOLS && arrival_order) {
+            io.bin_cursor = io.desc;  // nbins counters instead of tiles x nbins look-back descriptors
+            SVFM_CUDA(cudaMemsetAsync(io.desc, 0, (size_t)nbins * 4, s->stream));
+        } else if (part == PART_SYMBOLS) {
+            SVFM_CUDA(cudaMemsetAsync(io.desc, 0, n_tiles * nbins * 4, s->stream));
+        }
+        const size_t smem = part != PART_NONE ? sizeof(Item) * ROUND_TILE + (size_t)nbins * 16 + ((size_t)ROUND_WARPS * nbins + nbins) * 4 +
+                                                    0 : 0;
         auto launch = [&](auto kernel) -> int {
             // always the same value: concurrent sessions launch this kernel with different sizes, and the attribute is
             // per function, not per launch
@@ -334,10 +358,15 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
             SVFM_CUDA(cudaGetLastError());
             return SVFM_OK;
         };
-        if (r == 0 && part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, true>);
-        else if (r == 0) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, false>);
-        else if (part) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, true>);
-        else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, false>);
+        if (r == 0) {
+            if (part == PART_SYMBOLS) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_SYMBOLS>);
+            else if (part == PART_INDEX) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_INDEX>);
+            else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_NONE>);
+        } else {
+            if (part == PART_SYMBOLS) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_SYMBOLS>);
+            else if (part == PART_INDEX) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_INDEX>);
+            else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_NONE>);
+        }
         if (rc) return rc;
         if (r > 0 && !last) cur ^= 1;
     }
@@ -346,10 +375,10 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
 }
 
 template <class P, int NPL, int VBITS>
-static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
-                            void* d_cnt_work, const uint32_t** idx_out) {
-    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
-    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out);
+static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode, void* d_sp_work,
+                            void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {
+    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb);
+    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb);
 }
 
 template <class P>
@@ -375,12 +404,17 @@ static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_
 
 
 // LF-walk + sampled-SA lookup for every SA row of every pattern (SVFM_PHASE_LOCATE).
+// d_recs != NULL: bucket mode (search_kernels.cuh, "bucketed sort-back") -- records go to d_recs through d_cursor and
+// d_offs / d_positions / d_rec_key are unused.
 template <class P, int NPL, int VBITS>
 static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
-                      const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
+                      const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
+                      void* d_recs, unsigned long long* d_cursor) {
     if (total == 0) return SVFM_OK;
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
     HeavyList<P> heavy{nullptr, nullptr, nullptr, nullptr, s->d_counters + 1, 0};
+    BucketOut<P> bk{(SbRec<P>*)d_recs, d_cursor};
+    const bool bucket = d_recs != nullptr;
     int rc;
     if (heavy_seen) {
         if ((rc = s->heavy_sp.reserve(heavy_seen * sizeof(P))) || (rc = s->heavy_cnt.reserve((heavy_seen + 1) * sizeof(P))) ||
@@ -395,14 +429,17 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
     }
     {
         PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        auto launch = [&](auto kernel) {
+            const int grid = resident_grid(kernel, n, LOCATE_THREADS, s->ix->device);
+            kernel<<<grid, LOCATE_THREADS, 0, s->stream>>>(dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n,
+                                                           (P*)d_positions, d_rec_key, heavy, bk);
+        };
         if (dix.ilv) {
-            const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS, true>, n, LOCATE_THREADS, s->ix->device);
-            locate_warp_kernel<P, NPL, VBITS, true><<<grid, LOCATE_THREADS, 0, s->stream>>>(
-                dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+            if (bucket) launch(locate_warp_kernel<P, NPL, VBITS, true, true>);
+            else launch(locate_warp_kernel<P, NPL, VBITS, true, false>);
         } else {
-            const int grid = resident_grid(locate_warp_kernel<P, NPL, VBITS, false>, n, LOCATE_THREADS, s->ix->device);
-            locate_warp_kernel<P, NPL, VBITS, false><<<grid, LOCATE_THREADS, 0, s->stream>>>(
-                dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n, (P*)d_positions, d_rec_key, heavy);
+            if (bucket) launch(locate_warp_kernel<P, NPL, VBITS, false, true>);
+            else launch(locate_warp_kernel<P, NPL, VBITS, false, false>);
         }
         SVFM_CUDA(cudaGetLastError());
     }
@@ -417,14 +454,18 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
     if (blocks > 0x7fffffffull) return SVFM_ERR_TOO_LARGE;
     if (blocks) {
         PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
-        if (dix.ilv)
-            locate_rows_kernel<P, NPL, VBITS, true><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
-            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
-            (P*)d_positions, d_rec_key);
-        else
-            locate_rows_kernel<P, NPL, VBITS, false><<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(
-            dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase, heavy.pat, heavy_seen, heavy_total,
-            (P*)d_positions, d_rec_key);
+        auto launch = [&](auto kernel) {
+            kernel<<<(unsigned)blocks, LOCATE_THREADS, 0, s->stream>>>(dix, heavy.sp, (const uint64_t*)s->heavy_offs.ptr, heavy.obase,
+                                                                      heavy.pat, heavy_seen, heavy_total, (P*)d_positions, d_rec_key,
+                                                                      (SbRec<P>*)d_recs);
+        };
+        if (dix.ilv) {
+            if (bucket) launch(locate_rows_kernel<P, NPL, VBITS, true, true>);
+            else launch(locate_rows_kernel<P, NPL, VBITS, true, false>);
+        } else {
+            if (bucket) launch(locate_rows_kernel<P, NPL, VBITS, false, true>);
+            else launch(locate_rows_kernel<P, NPL, VBITS, false, false>);
+        }
         SVFM_CUDA(cudaGetLastError());
     }
     return SVFM_OK;
@@ -434,12 +475,13 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
 // ---- per-(Position, Vector) entry points; `planes` picks Block2..Block6 ------------------------------------------
 struct TypeOps {
     int (*search)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                  void* d_sp_work, void* d_cnt_work);
+                  void* d_sp_work, void* d_cnt_work, const SbOut& sb);
     int (*build_ext)(uint32_t planes, svfm_index* ix, uint64_t ext_bits);
-    int (*search_sweep)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort,
-                        void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out);
+    int (*search_sweep)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,
+                        void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb);
     int (*locate)(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
-                  const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key);
+                  const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
+                  void* d_recs, unsigned long long* d_cursor);
 };
 
 #define SVFM_PLANES_SWITCH(P, VB, FN, ...)          \
@@ -455,20 +497,21 @@ struct TypeOps {
 // One translation unit per (P, VB): defines `const TypeOps NAME`.
 #define SVFM_DEFINE_TYPE_OPS(NAME, P, VB)                                                                                          \
     static int NAME##_search(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx,   \
-                             uint32_t bits, void* d_sp_work, void* d_cnt_work) {                                                    \
-        SVFM_PLANES_SWITCH(P, VB, run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work)                                        \
+                             uint32_t bits, void* d_sp_work, void* d_cnt_work, const SbOut& sb) {                       \
+        SVFM_PLANES_SWITCH(P, VB, run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb)                               \
     }                                                                                                                               \
     static int NAME##_build_ext(uint32_t planes, svfm_index* ix, uint64_t ext_bits) {                                               \
         SVFM_PLANES_SWITCH(P, VB, run_build_ext, ix, ext_bits)                                                                      \
     }                                                                                                                               \
-    static int NAME##_search_sweep(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, \
-                                   void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out) {                                   \
-        SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out)                        \
+    static int NAME##_search_sweep(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,  \
+                                   void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {      \
+        SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb)               \
     }                                                                                                                               \
     static int NAME##_locate(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work,              \
                              const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen,                   \
-                             void* d_positions, uint32_t* d_rec_key) {                                                              \
-        SVFM_PLANES_SWITCH(P, VB, run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key)  \
+                             void* d_positions, uint32_t* d_rec_key, void* d_recs, unsigned long long* d_cursor) {                  \
+        SVFM_PLANES_SWITCH(P, VB, run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key,  \
+                           d_recs, d_cursor)                                                                                        \
     }                                                                                                                               \
     extern const TypeOps NAME;                                                                                                      \
     const TypeOps NAME = {NAME##_search, NAME##_build_ext, NAME##_search_sweep, NAME##_locate};

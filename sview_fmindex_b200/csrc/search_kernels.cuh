@@ -19,6 +19,14 @@ struct PatternBatch {
 
 constexpr int SEARCH_THREADS = 256;
 constexpr uint32_t HEAVY_ROWS = 1024;  // patterns with more SA rows than this are located row-parallel
+constexpr uint32_t SB_SHIFT = 12;      // bucketed sort-back: a bucket = 2^12 consecutive pattern indices (see SbRec below)
+constexpr uint32_t SB_BUCKET = 1u << SB_SHIFT;
+
+// Bucketed sort-back, sizing side (filled by the search kernels; see SbRec below).
+struct SbOut {
+    uint32_t* hist;             // per bucket: SA rows of its patterns (NULL: no bucketed sort-back for this batch)
+    unsigned long long* total;  // all rows of the batch (64 bits: tells the host when the 32-bit counters have wrapped)
+};
 
 // One backward-search step for both range ends: FmIndex::next_pos_range (locate/mod.rs:39-45) =
 // count_array[s] + get_next_rank(pos, s) (bwm/mod.rs:197-215) for pos in {sp, ep}.
@@ -113,6 +121,7 @@ struct SearchIO {
     P* cnt_out;             // work order, nullable
     unsigned long long* heavy_seen;  // nullable
     int* err;
+    SbOut sb;
 };
 
 // FmIndex::get_pos_range (locate/with_slice.rs:21-33) for one pattern per thread, grid-stride.
@@ -138,6 +147,7 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
     const uint32_t in_key = io.keys ? 64u / bits : 0u;  // symbols (from the end) available in the key
     const uint64_t sym_mask = (1ull << bits) - 1;
     int errbits = 0;
+    unsigned long long rows = 0;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < pb.n; w += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = io.idx ? (uint64_t)io.idx[w] : w;
         const uint64_t key = io.keys ? io.keys[w] : 0ull;
@@ -199,6 +209,15 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
         if (io.sp_out) io.sp_out[w] = sp;
         if (io.cnt_out) io.cnt_out[w] = cnt;
         if (io.heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);  // rare: sizes the heavy list
+        if (io.sb.hist && cnt != 0) {
+            atomicAdd(io.sb.hist + (i >> SB_SHIFT), (uint32_t)cnt);
+            rows += (unsigned long long)cnt;
+        }
+    }
+    if (io.sb.hist) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
+        if ((threadIdx.x & 31) == 0 && rows) atomicAdd(io.sb.total, rows);
     }
     if (errbits) atomicOr(io.err, errbits);
 }
@@ -430,11 +449,17 @@ constexpr int ROUND_THREADS = 256;
 #ifndef SVFM_ROUND_MIN_CTAS
 #define SVFM_ROUND_MIN_CTAS 5
 #endif
+#ifndef SVFM_ROUND_LB
+#define SVFM_ROUND_LB 0
+#endif
 constexpr int ROUND_ITEMS = SVFM_ROUND_ITEMS;               // items per thread
 constexpr int ROUND_TILE = ROUND_THREADS * ROUND_ITEMS;     // items per tile
 constexpr int ROUND_WARPS = ROUND_THREADS / 32;
 constexpr int ROUND_MAX_BINS = 512;
+constexpr int ROUND_LB = SVFM_ROUND_LB;                     // look-back: descriptors polled per thread and step (0: one
+                                                            // thread per digit walks back alone -- measured faster, see below)
 constexpr uint32_t DESC_AGG = 1u << 30, DESC_PREFIX = 2u << 30, DESC_MASK = (1u << 30) - 1;
+enum : int { PART_NONE = 0, PART_SYMBOLS = 1, PART_INDEX = 2 };
 
 template <class P, class R>
 struct SweepRoundIO {
@@ -448,11 +473,16 @@ struct SweepRoundIO {
     P* sp_out;
     P* cnt_out;
     uint32_t* idx_out;
-    // PART only
+    // PART_SYMBOLS only
     const uint32_t* hist;      // digit histogram of this round over the whole batch (pack_sweep_kernel), nbins entries
     uint32_t* desc;            // tiles x nbins look-back descriptors, zeroed before the launch
+    // PART_INDEX only: partition digit = idx >> idx_shift, bin b starts at min(n, b << idx_shift)
+    uint32_t idx_shift;
+    // PART_INDEX, and PART_SYMBOLS in arrival order (see below): nbins counters, zeroed before the launch
+    uint32_t* bin_cursor;
     uint32_t* tile_counter;    // zeroed before the launch
     unsigned long long* heavy_seen;
+    SbOut sb;                  // last round of `locate`: bucket sizes of the bucketed sort-back
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
@@ -464,15 +494,26 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// One round of the sweep search, fused with the radix partition that follows it (PART):
+// One round of the sweep search, fused with the radix partition that follows it:
 //   load a tile of items (FIRST: seed them from the extended table) -> `steps` backward steps each
-//   (with_slice.rs:27-31) -> digit = the symbols just consumed, last one most significant -> stable rank of every
-//   item inside its digit (warp match + per-warp counters) -> exclusive prefix of the digit counts over all earlier
-//   tiles by decoupled look-back (one descriptor word per tile and digit: flag | count) -> items leave through a
-//   shared-memory exchange so that every digit's run is written with coalesced stores.
+//   (with_slice.rs:27-31) -> partition digit -> stable rank of every item inside its digit (warp match + per-warp
+//   counters) -> position of the tile's items inside every digit's run -> items leave through a shared-memory exchange
+//   so that every digit's run is written with coalesced stores.
+// PART_SYMBOLS: digit = the symbols just consumed, last one most significant; exclusive prefix of the digit counts over all
+//   earlier tiles by decoupled look-back (one descriptor word per tile and digit: flag | count).  The digit depends on the
+//   pattern alone, so a tile publishes its counts BEFORE its backward steps.  With ROUND_LB > 0 the look-back polls a
+//   WINDOW of predecessors at once (256 / nbins threads per digit, ROUND_LB descriptors each); measured on B200 (10^8
+//   20-mers, two rounds): 5.83 ms with a window of 8 against 5.31 ms for one thread per digit walking back alone (16.6
+//   polls per tile on average) -- the two extra block barriers per window cost more than the shorter walk saves.
+//   With io.bin_cursor set, PART_SYMBOLS skips the look-back: a tile reserves its space inside every digit's run with one
+//   atomic add per digit, so the tiles of a run follow each other in ARRIVAL order instead of tile order.  Results never
+//   depend on the order of the work items; the runs stay sorted up to the few hundred tiles in flight at any time (each
+//   tile's share is sorted in itself), which is all the locality of the next round needs.
+// PART_INDEX (last round of `count`): digit = top bits of the caller's pattern index; order inside a digit does not
+//   matter (scatter_counts_kernel places by index), so a tile reserves its space with one atomic add per digit.
 // Tiles are handed out by an atomic counter, so a tile's predecessors are always running or done.
-// Without PART (last round of `count`) items are written back in place.
-template <class P, int NPL, int VBITS, class R, bool FIRST, bool PART>
+// PART_NONE: items are written back in place.
+template <class P, int NPL, int VBITS, class R, bool FIRST, int PART>
 __global__ void __launch_bounds__(ROUND_THREADS, SVFM_ROUND_MIN_CTAS)
 sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shift, uint32_t steps, uint32_t nbins,
                    const SweepRoundIO<P, R> io) {
@@ -482,22 +523,51 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     __shared__ uint8_t s_present[64];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_scan[ROUND_WARPS];
-    // dynamic: items[ROUND_TILE] | whist[ROUND_WARPS][nbins] | binstart[nbins] | tilebin[nbins] | gbase[nbins] (u64)
+    __shared__ uint64_t s_wsum[ROUND_WARPS];
+    __shared__ uint32_t s_lb[ROUND_THREADS * (ROUND_LB > 0 ? ROUND_LB : 1)];
+    // dynamic: items[ROUND_TILE] | gbase[nbins] (u64) | binstart[nbins] (u64) | whist[ROUND_WARPS][nbins] | tilebin[nbins]
     Item* s_items = reinterpret_cast<Item*>(s_dyn);
     uint64_t* s_gbase = reinterpret_cast<uint64_t*>(s_dyn + sizeof(Item) * ROUND_TILE);
     uint64_t* s_binstart = s_gbase + nbins;
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_binstart + nbins);
     uint32_t* s_tilebin = s_whist + ROUND_WARPS * nbins;
+    unsigned long long rows = 0;
 
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_present[i] = ix.present[i];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
-    if (PART) {
-        // global start of every digit = exclusive scan of the batch histogram (serial per warp-chunk; nbins <= 512)
-        if (threadIdx.x == 0) {
-            uint64_t acc = 0;
-            for (uint32_t b = 0; b < nbins; b++) { s_binstart[b] = acc; acc += io.hist[b]; }
+    if constexpr (PART == PART_SYMBOLS) {
+        // global start of every digit = exclusive scan of the batch histogram (nbins <= 512: two values per thread)
+        uint32_t v[ROUND_MAX_BINS / ROUND_THREADS];
+        uint64_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < ROUND_MAX_BINS / ROUND_THREADS; i++) {
+            const uint32_t b = threadIdx.x * (ROUND_MAX_BINS / ROUND_THREADS) + i;
+            v[i] = b < nbins ? io.hist[b] : 0u;
+            sum += v[i];
+        }
+        uint64_t incl = sum;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint64_t o = __shfl_up_sync(full, incl, dlt);
+            if ((int)lane >= dlt) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint64_t run = incl - sum;
+        for (uint32_t w = 0; w < warp; w++) run += s_wsum[w];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ROUND_MAX_BINS / ROUND_THREADS; i++) {
+            const uint32_t b = threadIdx.x * (ROUND_MAX_BINS / ROUND_THREADS) + i;
+            if (b < nbins) s_binstart[b] = run;
+            run += v[i];
+        }
+    } else if constexpr (PART == PART_INDEX) {
+        for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+            const uint64_t st = (uint64_t)b << io.idx_shift;
+            s_binstart[b] = st < n ? st : n;
         }
     }
     __syncthreads();
@@ -541,13 +611,14 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         // published BEFORE the backward steps: by the time this tile looks back, its predecessors have long done so too.
         uint32_t rank[ROUND_ITEMS], dig[ROUND_ITEMS];
         uint32_t* my_hist = s_whist + warp * nbins;
-        if constexpr (PART) {
+        if constexpr (PART != PART_NONE) {
             for (uint32_t i = threadIdx.x; i < ROUND_WARPS * nbins; i += ROUND_THREADS) s_whist[i] = 0;
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < ROUND_ITEMS; k++) {
                 const bool valid = base + (uint64_t)k * 32 < n;
-                dig[k] = valid ? (uint32_t)((rest[k] >> shift) & digit_mask) : 0xffffffffu;
+                if constexpr (PART == PART_INDEX) dig[k] = valid ? (idx[k] >> io.idx_shift) : 0xffffffffu;
+                else dig[k] = valid ? (uint32_t)((rest[k] >> shift) & digit_mask) : 0xffffffffu;
                 const unsigned peers = __match_any_sync(full, dig[k]);
                 const int leader = __ffs(peers) - 1;
                 uint32_t before = 0;
@@ -569,7 +640,10 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                     acc += t;
                 }
                 s_tilebin[b] = acc;
-                st_volatile_u32(io.desc + tile * nbins + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+                if (PART == PART_SYMBOLS && !io.bin_cursor)
+                    st_volatile_u32(io.desc + tile * nbins + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+                else
+                    s_gbase[b] = s_binstart[b] + (acc ? atomicAdd(io.bin_cursor + b, acc) : 0u);
             }
         }
         // ---- backward steps
@@ -582,8 +656,12 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 cnt[k] = (P)(ep - sp[k]);
             }
             if (io.heavy_seen && (uint64_t)cnt[k] > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);
+            if (io.sb.hist && cnt[k] != 0) {
+                atomicAdd(io.sb.hist + (idx[k] >> SB_SHIFT), (uint32_t)cnt[k]);
+                rows += (unsigned long long)cnt[k];
+            }
         }
-        if constexpr (!PART) {
+        if constexpr (PART == PART_NONE) {
 #pragma unroll
             for (int k = 0; k < ROUND_ITEMS; k++) {
                 const uint64_t w = base + (uint64_t)k * 32;
@@ -595,20 +673,54 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 }
             }
         } else {
+        if (PART == PART_SYMBOLS && !io.bin_cursor) {
         // ---- look-back over the earlier tiles (decoupled: aggregate or inclusive prefix per tile and digit)
-        for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+        if (ROUND_LB > 0 && nbins <= (uint32_t)ROUND_THREADS) {
+            // thread (b, j) polls the predecessors at distance j+1, j+1+W, ... of the window for digit b (W threads per digit)
+            const uint32_t b = threadIdx.x & (nbins - 1u), j = threadIdx.x / nbins, W = ROUND_THREADS / nbins;
             uint32_t excl = 0;
-            const uint32_t acc = s_tilebin[b];
-            if (tile > 0) {
-                for (uint64_t t = tile - 1;; t--) {
-                    uint32_t v;
-                    do { v = ld_volatile_u32(io.desc + t * nbins + b); } while ((v >> 30) == 0);
-                    excl += v & DESC_MASK;
-                    if ((v >> 30) == 2u || t == 0) break;
+            bool done = tile == 0;
+            for (uint64_t far = 0; tile > 0; far += (uint64_t)W * ROUND_LB) {  // predecessors tile-1-far .. tile-far-W*LB
+#pragma unroll
+                for (int l = 0; l < ROUND_LB; l++) {
+                    const uint64_t d = far + j + (uint64_t)l * W;  // distance - 1
+                    uint32_t v = DESC_PREFIX;                       // before tile 0: an empty prefix
+                    if (d < tile) {
+                        const uint32_t* q = io.desc + (tile - 1 - d) * nbins + b;
+                        do { v = ld_volatile_u32(q); } while ((v >> 30) == 0);
+                    }
+                    s_lb[(j + l * W) * nbins + b] = v;
                 }
-                st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + acc));
+                __syncthreads();
+                if (j == 0 && !done) {
+                    for (uint32_t d = 0; d < W * ROUND_LB; d++) {
+                        const uint32_t v = s_lb[d * nbins + b];
+                        excl += v & DESC_MASK;
+                        if ((v >> 30) == 2u) { done = true; break; }
+                    }
+                }
+                if (__syncthreads_and(j != 0 || done)) break;
             }
-            s_gbase[b] = s_binstart[b] + excl;
+            if (j == 0) {
+                if (tile > 0) st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + s_tilebin[b]));
+                s_gbase[b] = s_binstart[b] + excl;
+            }
+        } else {
+            for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+                uint32_t excl = 0;
+                const uint32_t acc = s_tilebin[b];
+                if (tile > 0) {
+                    for (uint64_t t = tile - 1;; t--) {
+                        uint32_t v;
+                        do { v = ld_volatile_u32(io.desc + t * nbins + b); } while ((v >> 30) == 0);
+                        excl += v & DESC_MASK;
+                        if ((v >> 30) == 2u || t == 0) break;
+                    }
+                    st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + acc));
+                }
+                s_gbase[b] = s_binstart[b] + excl;
+            }
+        }
         }
         __syncthreads();
         // exclusive scan of the tile totals over the digits (position of every digit's run inside the exchange buffer)
@@ -652,7 +764,10 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         const uint32_t tile_n = (uint32_t)(n - tile * ROUND_TILE < (uint64_t)ROUND_TILE ? n - tile * ROUND_TILE : (uint64_t)ROUND_TILE);
         for (uint32_t j = threadIdx.x; j < tile_n; j += ROUND_THREADS) {
             const Item v = s_items[j];
-            const uint64_t g = s_gbase[(uint32_t)((v.rest >> shift) & digit_mask)] + j;
+            uint32_t d;
+            if constexpr (PART == PART_INDEX) d = v.idx >> io.idx_shift;
+            else d = (uint32_t)((v.rest >> shift) & digit_mask);
+            const uint64_t g = s_gbase[d] + j;
             if (io.items_out) io.items_out[g] = v;
             if (io.sp_out) io.sp_out[g] = v.sp;
             if (io.cnt_out) io.cnt_out[g] = v.cnt;
@@ -660,6 +775,11 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         }
         __syncthreads();
         }  // PART
+    }
+    if (io.sb.hist) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(full, rows, d);
+        if (lane == 0 && rows) atomicAdd(io.sb.total, rows);
     }
 }
 
@@ -715,20 +835,39 @@ struct HeavyList {
     uint64_t capacity;
 };
 
-// Locate for patterns in work order: work item w has SA rows sp_work[w] .. +cnt_work[w] and writes the
-// position of row sp+j at positions[offs[w] + j] (offs = exclusive prefix sums of cnt_work), i.e. in SA-row
-// order inside a pattern (the reference's order, locate/mod.rs:19).  In record mode (rec_key != NULL) it also
-// writes rec_key[offs[w] + j] = idx[w], the caller's pattern index, so that a stable sort by rec_key brings
-// the positions into the caller's CSR order without any random scatter.
+// ---- bucketed sort-back (locate results -> the caller's CSR order without a radix sort) ---------------------------
+// The locate kernels emit (pattern index, position) records straight into BUCKETS of 2^SB_SHIFT consecutive pattern
+// indices.  The bucket sizes are known before locate starts (SbOut: the search kernels sum the counts per bucket), so a
+// pattern reserves its cnt consecutive slots with ONE atomic add on its bucket's cursor and its rows land there in
+// SA-row order (locate/mod.rs:19).  A bucket ends up holding every record of 4096 consecutive patterns, each pattern's
+// records contiguous; sb_place_kernel finishes inside shared memory.  Writes go to ~n/4096 write fronts that advance
+// monotonically, which L2 merges into full lines; nothing is sorted.  (Reserving the slots in the search kernel instead
+// -- no atomic in locate -- was measured: 6.7 ms instead of 4.6 ms, because a bucket's records then arrive in an order
+// unrelated to their addresses and every 8-byte store becomes a partial DRAM sector write.)
+template <class P> struct SbRec;
+template <> struct alignas(8) SbRec<uint32_t> { uint32_t pos; uint32_t idx; };
+template <> struct alignas(16) SbRec<uint64_t> { uint64_t pos; uint32_t idx; uint32_t pad; };
+
+template <class P>
+struct BucketOut {
+    SbRec<P>* recs;                // total records, bucket b at [base[b], base[b+1])
+    unsigned long long* cursor;    // per bucket: next free record slot (starts at base[b])
+};
+
+// Locate for patterns in work order: work item w has SA rows sp_work[w] .. +cnt_work[w].
+// CSR mode (BUCKET = false): the position of row sp+j goes to positions[offs[w] + j] (offs = exclusive prefix sums of
+// cnt_work), i.e. in SA-row order inside a pattern (the reference's order, locate/mod.rs:19); with rec_key != NULL also
+// rec_key[offs[w] + j] = idx[w] (records for the radix sort-back, SVFM_SORTED only).
+// Bucket mode (BUCKET = true): see above; offs / positions / rec_key are unused.
 // One warp owns 32 consecutive work items and spreads ALL their rows over its lanes (warp prefix sum of the
 // counts, then each lane finds the owner of its row with a shuffle binary search), so a pattern with many
 // rows does not serialise one lane.  Patterns with more than HEAVY_ROWS rows are deferred to
 // locate_rows_kernel through the heavy list.
-template <class P, int NPL, int VBITS, bool ILV>
+template <class P, int NPL, int VBITS, bool ILV, bool BUCKET>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
                    const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
-                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy) {
+                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy, BucketOut<P> bk) {
     __shared__ P s_count[65];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     __syncthreads();
@@ -746,8 +885,9 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
             const P cw = cnt_work[w];
             if (cw != 0) {
                 sp = sp_work[w];
-                obase = offs[w];
                 pat = idx ? idx[w] : (uint32_t)w;
+                if constexpr (BUCKET) obase = atomicAdd(bk.cursor + (pat >> SB_SHIFT), (unsigned long long)cw);
+                else obase = offs[w];
                 if ((uint64_t)cw > HEAVY_ROWS) {
                     const unsigned long long h = atomicAdd(heavy.n, 1ull);
                     if (h < heavy.capacity) { heavy.sp[h] = sp; heavy.cnt[h] = cw; heavy.obase[h] = obase; heavy.pat[h] = pat; }
@@ -756,12 +896,21 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
                 }
             }
         }
+        auto emit = [&](uint64_t at, P pos, uint32_t pattern) {
+            if constexpr (BUCKET) {
+                SbRec<P> r;
+                r.pos = pos;
+                r.idx = pattern;
+                if constexpr (sizeof(P) == 8) r.pad = 0;
+                bk.recs[at] = r;
+            } else {
+                positions[at] = pos;
+                if (rec_key) rec_key[at] = pattern;
+            }
+        };
         if (__all_sync(full, c <= 1u)) {
             // common case: at most one row per pattern, no redistribution needed
-            if (c) {
-                positions[obase] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp);
-                if (rec_key) rec_key[obase] = pat;
-            }
+            if (c) emit(obase, locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp), pat);
             continue;
         }
         uint32_t incl = c;
@@ -788,8 +937,7 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
             const uint32_t opat = __shfl_sync(full, pat, o);
             if (r < total) {
                 const uint32_t j = r - e;
-                positions[oo + j] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j));
-                if (rec_key) rec_key[oo + j] = opat;
+                emit(oo + j, locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j)), opat);
             }
         }
     }
@@ -798,11 +946,11 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
 // Row-parallel locate for the heavy list: one thread per SA row; row t belongs to the entry h with
 // offs[h] <= t < offs[h+1].  The per-block window of candidate entries is found once with two binary
 // searches; each thread then searches only that window.
-template <class P, int NPL, int VBITS, bool ILV>
+template <class P, int NPL, int VBITS, bool ILV, bool BUCKET>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_t* __restrict__ offs,
                    const uint64_t* __restrict__ obase, const uint32_t* __restrict__ pat, uint64_t n, uint64_t total,
-                   P* __restrict__ positions, uint32_t* __restrict__ rec_key) {
+                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, SbRec<P>* __restrict__ recs) {
     __shared__ P s_count[65];
     __shared__ uint64_t s_win[2];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
@@ -828,8 +976,159 @@ locate_rows_kernel(const DevIndex<P> ix, const P* __restrict__ sp, const uint64_
     const uint64_t j = t - __ldg(offs + lo);
     const P row = (P)(__ldg(sp + lo) + (P)j);
     const uint64_t dst = __ldg(obase + lo) + j;
-    positions[dst] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, row);
-    if (rec_key) rec_key[dst] = __ldg(pat + lo);
+    const P pos = locate_row<P, NPL, VBITS, ILV>(ix, s_count, row);
+    if constexpr (BUCKET) {
+        SbRec<P> r;
+        r.pos = pos;
+        r.idx = __ldg(pat + lo);
+        if constexpr (sizeof(P) == 8) r.pad = 0;
+        recs[dst] = r;
+    } else {
+        positions[dst] = pos;
+        if (rec_key) rec_key[dst] = __ldg(pat + lo);
+    }
+}
+
+// Bucket bases: exclusive prefix sums of the per-bucket record counts (one CTA; nb <= a few 10^5).
+// base[0..nb], base[nb] = total records; cursor[b] = base[b].
+constexpr int SB_SCAN_THREADS = 1024;
+static __global__ void __launch_bounds__(SB_SCAN_THREADS)
+sb_scan_kernel(const uint32_t* __restrict__ hist, uint64_t nb, uint64_t* __restrict__ base, unsigned long long* __restrict__ cursor) {
+    __shared__ uint64_t s_warp[SB_SCAN_THREADS / 32];
+    __shared__ uint64_t s_carry;
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t b0 = 0; b0 < nb; b0 += SB_SCAN_THREADS) {
+        const uint64_t b = b0 + threadIdx.x;
+        const uint64_t v = b < nb ? (uint64_t)hist[b] : 0ull;
+        uint64_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_up_sync(full, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint64_t off = s_carry;
+        for (uint32_t w = 0; w < warp; w++) off += s_warp[w];
+        const uint64_t excl = off + incl - v;
+        if (b < nb) { base[b] = excl; cursor[b] = excl; }
+        __syncthreads();
+        if (threadIdx.x == SB_SCAN_THREADS - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base[nb] = s_carry;
+}
+
+// One CTA per bucket: CSR offsets of the bucket's patterns and the final place of every record.
+// Every pattern's records are contiguous inside the bucket and in SA-row order (see BucketOut), so the run boundaries
+// give first[k] / end[k] of pattern k with plain shared-memory stores -- no atomics, no dependence on the order in which
+// the patterns arrived.  out_offs[i] = base[bucket] + (exclusive prefix sum of the run lengths in pattern order);
+// record p of pattern k goes to positions[out_offs[k] + (p - first[k])], through a shared-memory staging buffer when the
+// bucket fits it, so that the global stores are coalesced.
+// The per-pattern arrays are padded by one word per 32 (index k lives at k + k/32): a thread then owns 32 consecutive
+// patterns without bank conflicts, and the scan needs one pass instead of one barrier pair per 256 patterns.
+// A bucket must hold fewer than 2^32 records (the host falls back to the radix sort-back above 2^32 in total).
+constexpr int SB_PLACE_THREADS = 256;
+constexpr uint32_t SB_PAD = SB_BUCKET + SB_BUCKET / 32;
+constexpr uint32_t SB_STAGE = SB_BUCKET + SB_BUCKET / 2;   // records staged in shared memory (6144; a bucket averages occ x 4096)
+constexpr size_t SB_PLACE_SMEM = (2 * (size_t)SB_PAD) * 4;  // + SB_STAGE * sizeof(P)
+__device__ __forceinline__ uint32_t sb_pad(uint32_t k) { return k + (k >> 5); }
+template <class P>
+__global__ void __launch_bounds__(SB_PLACE_THREADS)
+sb_place_kernel(const SbRec<P>* __restrict__ recs, const uint64_t* __restrict__ base, uint64_t n, uint64_t nb,
+                void* __restrict__ out_offs, int offs32, P* __restrict__ positions) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint32_t* s_first = reinterpret_cast<uint32_t*>(s_dyn);          // SB_PAD
+    uint32_t* s_off = s_first + SB_PAD;                               // SB_PAD: end[k], then exclusive offset of k
+    P* s_pos = reinterpret_cast<P*>(s_off + SB_PAD);                  // SB_STAGE
+    __shared__ uint32_t s_warp[SB_PLACE_THREADS / 32];
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t b = blockIdx.x;
+    const uint64_t r0 = base[b];
+    const uint32_t m = (uint32_t)(base[b + 1] - r0);                  // records of this bucket
+    const uint64_t p0 = b << SB_SHIFT;                                // first pattern of this bucket
+    const uint32_t np = (uint32_t)(n - p0 < (uint64_t)SB_BUCKET ? n - p0 : (uint64_t)SB_BUCKET);
+    for (uint32_t k = threadIdx.x; k < SB_PAD; k += SB_PLACE_THREADS) { s_first[k] = 0; s_off[k] = 0; }
+    __syncthreads();
+    const SbRec<P>* rb = recs + r0;
+    // ---- run boundaries
+    for (uint32_t q0 = 0; q0 < m; q0 += SB_PLACE_THREADS) {
+        const uint32_t p = q0 + threadIdx.x;
+        const bool valid = p < m;
+        const uint32_t k = valid ? (rb[p].idx & (SB_BUCKET - 1)) : 0xffffffffu;
+        uint32_t k_prev = __shfl_up_sync(full, k, 1);
+        uint32_t k_next = __shfl_down_sync(full, k, 1);
+        if (lane == 0) k_prev = (valid && p > 0) ? (rb[p - 1].idx & (SB_BUCKET - 1)) : 0xffffffffu;
+        if (lane == 31) k_next = (valid && p + 1 < m) ? (rb[p + 1].idx & (SB_BUCKET - 1)) : 0xffffffffu;
+        if (valid) {
+            if (k != k_prev) s_first[sb_pad(k)] = p;
+            if (k != k_next) s_off[sb_pad(k)] = p + 1;   // end of the run
+        }
+    }
+    __syncthreads();
+    // ---- exclusive prefix sums of the run lengths, in pattern order: thread t owns patterns [t*PER, (t+1)*PER)
+    constexpr uint32_t PER = SB_BUCKET / SB_PLACE_THREADS;
+    static_assert(PER <= 32 && 32 % PER == 0, "a thread's patterns stay inside one padding group");
+    {
+        const uint32_t a0 = sb_pad(threadIdx.x * PER);
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < PER; i++) sum += s_off[a0 + i] - s_first[a0 + i];   // patterns without records: 0 - 0
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(full, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (uint32_t w = 0; w < warp; w++) run += s_warp[w];
+#pragma unroll
+        for (uint32_t i = 0; i < PER; i++) {
+            const uint32_t v = s_off[a0 + i] - s_first[a0 + i];
+            s_off[a0 + i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < np; k += SB_PLACE_THREADS) {
+        const uint64_t o = r0 + s_off[sb_pad(k)];
+        if (offs32) reinterpret_cast<uint32_t*>(out_offs)[p0 + k] = (uint32_t)o;
+        else reinterpret_cast<uint64_t*>(out_offs)[p0 + k] = o;
+    }
+    if (b + 1 == nb && threadIdx.x == 0) {
+        if (offs32) reinterpret_cast<uint32_t*>(out_offs)[n] = (uint32_t)base[nb];
+        else reinterpret_cast<uint64_t*>(out_offs)[n] = base[nb];
+    }
+    // ---- placement
+    P* out = positions + r0;
+    const bool staged = m <= SB_STAGE;
+    for (uint32_t p = threadIdx.x; p < m; p += SB_PLACE_THREADS) {
+        const SbRec<P> r = rb[p];
+        const uint32_t k = sb_pad(r.idx & (SB_BUCKET - 1));
+        const uint32_t slot = s_off[k] + (p - s_first[k]);
+        if (staged) s_pos[slot] = r.pos;
+        else out[slot] = r.pos;
+    }
+    if (staged) {
+        __syncthreads();
+        for (uint32_t p = threadIdx.x; p < m; p += SB_PLACE_THREADS) out[p] = s_pos[p];
+    }
+}
+
+// counts_out[idx[w]] = cnt[w]: the work items arrive grouped by the top bits of idx (the last sweep round of `count`
+// partitions by them), so the scattered 4/8-byte stores of the CTAs running at any time fall into a window of a few MB
+// that L2 turns into full-line writes.
+template <class P>
+__global__ void __launch_bounds__(256)
+scatter_counts_kernel(const uint32_t* __restrict__ idx, const P* __restrict__ cnt, uint64_t n, P* __restrict__ counts_out) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x)
+        counts_out[idx[w]] = cnt[w];
 }
 
 // CSR offsets from the pattern indices of the records once they are sorted by pattern: first[k] = index of

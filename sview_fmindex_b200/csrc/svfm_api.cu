@@ -132,7 +132,7 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     s->ix = ix;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_err, sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(uint64_t), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         g_last_error = std::string("session_new: ") + cudaGetErrorString(e);
@@ -223,6 +223,10 @@ static uint64_t ext_bits_for(const svfm_index* ix) {
 }
 static std::atomic<uint64_t> g_ilv{[] {  // build the interleaved occ copy at load
     const char* e = std::getenv("SVFM_ILV");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
+}()};
+static std::atomic<uint64_t> g_bucket_sortback{[] {  // 1: bucketed sort-back (search_kernels.cuh), 0: radix sort-back
+    const char* e = std::getenv("SVFM_BUCKET_SORTBACK");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
 static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once more after the last round
@@ -429,14 +433,15 @@ static const TypeOps* type_ops(const svfm_type& t) {
 #define SVFM_BY_POS(FN, ...) (s->ix->type.pos_bits == 32 ? FN<uint32_t>(__VA_ARGS__) : FN<uint64_t>(__VA_ARGS__))
 
 static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                           void* d_sp_work, void* d_cnt_work) {
+                           void* d_sp_work, void* d_cnt_work, const SbOut& sb = SbOut{}) {
     const TypeOps* ops = type_ops(s->ix->type);
-    return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work) : SVFM_ERR_BAD_TYPE;
+    return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb) : SVFM_ERR_BAD_TYPE;
 }
-static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, bool final_sort, void* d_sp_work,
-                                 void* d_cnt_work, const uint32_t** idx_out) {
+static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode, void* d_sp_work,
+                                 void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb = SbOut{}) {
     const TypeOps* ops = type_ops(s->ix->type);
-    return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_sort, d_sp_work, d_cnt_work, idx_out) : SVFM_ERR_BAD_TYPE;
+    return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb)
+               : SVFM_ERR_BAD_TYPE;
 }
 // Interleaved occ copy: { block q | checkpoint row q } per aligned slot.  Derived from the blob, bytes only.
 static int build_ilv_table(svfm_index* ix) {
@@ -471,10 +476,33 @@ static int build_ext_table(svfm_index* ix) {
     return ops ? ops->build_ext(ix->type.planes, ix, ext_bits_for(ix)) : SVFM_ERR_BAD_TYPE;
 }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
-                           const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key) {
+                           const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
+                           void* d_recs = nullptr, unsigned long long* d_cursor = nullptr) {
     const TypeOps* ops = type_ops(s->ix->type);
-    return ops ? ops->locate(s->ix->type.planes, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key)
+    return ops ? ops->locate(s->ix->type.planes, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key,
+                             d_recs, d_cursor)
                : SVFM_ERR_BAD_TYPE;
+}
+// Bucketed sort-back, second half (search_kernels.cuh): CSR offsets + final place of every record, one CTA per bucket.
+template <class P>
+static int run_sb_place(svfm_session* s, uint64_t n, uint64_t nb, void* d_out_offs, bool offs32, void* d_positions) {
+    const size_t smem = SB_PLACE_SMEM + (size_t)SB_STAGE * sizeof(P);
+    SVFM_CUDA(cudaFuncSetAttribute(sb_place_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PhaseTimer pt(s, SVFM_PHASE_OTHER, 1);
+    sb_place_kernel<P><<<(unsigned)nb, SB_PLACE_THREADS, smem, s->stream>>>((const SbRec<P>*)s->sb_recs.ptr, (const uint64_t*)s->sb_base.ptr,
+                                                                           n, nb, d_out_offs, offs32 ? 1 : 0, (P*)d_positions);
+    SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+template <class P>
+static int run_scatter_counts(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_cnt_work, void* d_counts_out) {
+    PhaseTimer pt(s, SVFM_PHASE_OTHER, 1);
+    scatter_counts_kernel<P><<<grid_for(n, 256, s->ix->device), 256, 0, s->stream>>>(idx, (const P*)d_cnt_work, n, (P*)d_counts_out);
+    SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+__global__ void narrow_offs_kernel(const uint64_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
 }
 static int dispatch_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_out_offs) {
     return SVFM_BY_POS(run_scan, s, n, d_cnt, d_out_offs);
@@ -493,11 +521,12 @@ static int err_from_bits(int bits) {
     return SVFM_OK;
 }
 
-// Device-resident count: small batches run the search kernel in the caller's order; large ones are
-// locality-sorted first and the counts are sorted back.  Leaves the error bits in s->d_err.
+// Device-resident count: small batches run the search kernel in the caller's order; dense fixed-length batches take the
+// sweep search, whose last round groups the items by the top bits of the pattern index so that one scatter pass puts the
+// counts back in the caller's order; the locality-sorted generic path sorts them back.  Leaves the error bits in s->d_err.
 static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_out) {
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
-    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
+    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
     if (pb.n == 0) return SVFM_OK;
     const SortPlan plan = plan_sort(s->ix, pb.n, pb);
     if (!plan.sorted && !plan.sweep) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
@@ -508,7 +537,9 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
     if (plan.sweep) {
         if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
-        if ((rc = dispatch_search_sweep(s, pb, plan, false, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
+        const bool by_index = g_bucket_sortback.load() != 0;
+        if ((rc = dispatch_search_sweep(s, pb, plan, by_index ? PART_INDEX : PART_NONE, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
+        if (by_index) return SVFM_BY_POS(run_scatter_counts, s, pb.n, idx, s->cnt.ptr, d_counts_out);
     } else {
         if ((rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
         if ((rc = dispatch_search(s, pb, keys, idx, plan.bits, nullptr, s->cnt.ptr))) return rc;
@@ -518,30 +549,77 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
 
 // Device-resident locate pipeline.
 //   small batch : search -> scan -> (sync: total) -> LF-walk straight into CSR order [-> sort by position]
-//   large batch : locality sort -> search -> scan (work order) -> (sync: total) -> LF-walk into records
-//                 (pattern index, position) [-> sort by position] -> stable sort by pattern index -> CSR offsets
-static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags, uint64_t* d_out_offs,
+//   large batch : reorder (sweep search, or locality sort + search kernel); the search also sums the counts per bucket of
+//                 8192 pattern indices -> bucket bases -> (sync: total) -> LF-walk, records straight into their bucket
+//                 -> sb_place_kernel: CSR offsets + positions in the caller's order          ("bucketed sort-back")
+//   SVFM_SORTED on a large batch, or 2^32 and more occurrences: scan (work order) -> LF-walk into records -> radix sort
+//                 by position -> stable radix sort by pattern index -> CSR offsets
+// d_out_offs: u64[n+1], or u32[n+1] with SVFM_OFFS32 (SVFM_ERR_TOO_LARGE when the total does not fit).
+static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags, void* d_out_offs,
                          void** d_positions, uint64_t* total_out) {
     const uint64_t P = s->ix->type.pos_bits / 8;
     int rc;
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
-    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 2 * sizeof(unsigned long long), s->stream));
+    SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
     if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
     if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
     const SortPlan plan = plan_sort(s->ix, pb.n, pb);
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
-    uint64_t* offs_work = d_out_offs;  // small batch: work order == caller order
+    const bool offs32 = (flags & SVFM_OFFS32) != 0;
+    const bool by_position = (flags & SVFM_SORTED) != 0;
     const bool reordered = plan.sorted || plan.sweep;
+    bool bucket = reordered && !by_position && g_bucket_sortback.load() != 0;
+    const uint64_t nb = (pb.n + SB_BUCKET - 1) >> SB_SHIFT;
+    SbOut sb{};
+    if (bucket) {
+        if ((rc = s->sb_hist.reserve(nb * 4)) || (rc = s->sb_base.reserve((nb + 1) * 8)) || (rc = s->sb_cursor.reserve(nb * 8))) return rc;
+        sb.hist = (uint32_t*)s->sb_hist.ptr;
+        sb.total = s->d_counters + 2;
+        SVFM_CUDA(cudaMemsetAsync(sb.hist, 0, nb * 4, s->stream));
+    }
+    if (plan.sweep) {
+        if ((rc = dispatch_search_sweep(s, pb, plan, g_sweep_final_sort.load() != 0 ? PART_SYMBOLS : PART_NONE, s->sp.ptr, s->cnt.ptr,
+                                        &idx, sb)))
+            return rc;
+    } else {
+        if (plan.sorted && (rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
+        if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr, sb))) return rc;
+    }
+    if (bucket) {
+        {
+            PhaseTimer pt(s, SVFM_PHASE_SCAN, 1);
+            sb_scan_kernel<<<1, SB_SCAN_THREADS, 0, s->stream>>>(sb.hist, nb, (uint64_t*)s->sb_base.ptr, (unsigned long long*)s->sb_cursor.ptr);
+            SVFM_CUDA(cudaGetLastError());
+        }
+        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], s->d_counters + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[3], s->d_counters, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        if ((rc = err_from_bits((int)(s->h_pinned[1] & 0xffffffffu)))) return rc;
+        const uint64_t total = s->h_pinned[0];
+        const uint64_t heavy_seen = s->h_pinned[3];
+        *total_out = total;
+        if (total < 0xffffffffull) {  // the 32-bit bucket counters did not wrap
+            const uint64_t rec_bytes = P == 4 ? 8 : 16;
+            if ((rc = s->positions.reserve((total + 1) * P)) || (rc = s->sb_recs.reserve((total + 1) * rec_bytes))) return rc;
+            *d_positions = s->positions.ptr;
+            if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, nullptr, total, heavy_seen, nullptr, nullptr, s->sb_recs.ptr,
+                                      (unsigned long long*)s->sb_cursor.ptr)))
+                return rc;
+            return SVFM_BY_POS(run_sb_place, s, pb.n, nb, d_out_offs, offs32, s->positions.ptr);
+        }
+        bucket = false;  // 2^32 records and more: radix sort-back
+    }
+    uint64_t* offs_final = (uint64_t*)d_out_offs;  // u64 CSR offsets in the caller's order
+    if (offs32) {
+        if ((rc = s->offs64.reserve((pb.n + 1) * 8))) return rc;
+        offs_final = (uint64_t*)s->offs64.ptr;
+    }
+    uint64_t* offs_work = offs_final;  // small batch: work order == caller order
     if (reordered) {
         if ((rc = s->woffs.reserve((pb.n + 1) * 8))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
-    }
-    if (plan.sweep) {
-        if ((rc = dispatch_search_sweep(s, pb, plan, g_sweep_final_sort.load() != 0, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
-    } else {
-        if (plan.sorted && (rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
-        if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr))) return rc;
     }
     if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], offs_work + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
@@ -552,15 +630,20 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     const uint64_t total = s->h_pinned[0];
     const uint64_t heavy_seen = s->h_pinned[3];
     *total_out = total;
+    if (offs32 && total > 0xffffffffull) return SVFM_ERR_TOO_LARGE;
     if ((rc = s->positions.reserve((total + 1) * P))) return rc;
-    const bool by_position = (flags & SVFM_SORTED) != 0;
     const bool records = reordered || by_position;
     if (records && (rc = s->rec_key.reserve((total + 1) * 4))) return rc;
     *d_positions = s->positions.ptr;
     if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, offs_work, total, heavy_seen, s->positions.ptr,
                               records ? (uint32_t*)s->rec_key.ptr : nullptr)))
         return rc;
-    if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, reordered, d_out_offs, d_positions))) return rc;
+    if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, reordered, offs_final, d_positions))) return rc;
+    if (offs32) {
+        narrow_offs_kernel<<<grid_for(pb.n + 1, 256, s->ix->device), 256, 0, s->stream>>>(offs_final, pb.n + 1, (uint32_t*)d_out_offs);
+        g_launches++;
+        SVFM_CUDA(cudaGetLastError());
+    }
     return SVFM_OK;
 }
 
@@ -1238,7 +1321,7 @@ int svfm_count_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64
 }
 
 int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t n,
-                             uint32_t fixed_len, uint32_t flags, uint64_t* d_out_offs, void** d_positions,
+                             uint32_t fixed_len, uint32_t flags, void* d_out_offs, void** d_positions,
                              uint64_t* total) {
     if (!s || !d_out_offs || !d_positions || !total || (n && !d_pats)) return SVFM_ERR_BAD_ARG;
     if (!d_offs && fixed_len == 0 && n) return SVFM_ERR_EMPTY_PATTERN;
@@ -1246,7 +1329,7 @@ int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint6
     *total = 0;
     *d_positions = nullptr;
     if (n == 0) {
-        SVFM_CUDA(cudaMemsetAsync(d_out_offs, 0, sizeof(uint64_t), s->stream));
+        SVFM_CUDA(cudaMemsetAsync(d_out_offs, 0, (flags & SVFM_OFFS32) ? sizeof(uint32_t) : sizeof(uint64_t), s->stream));
         return SVFM_OK;
     }
     PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
@@ -1271,6 +1354,7 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_EXT_BITS: g_ext_bits.store(value); return SVFM_OK;
         case SVFM_TUNE_WORKERS: g_host_workers.store(value); return SVFM_OK;
         case SVFM_TUNE_ILV: g_ilv.store(value); return SVFM_OK;
+        case SVFM_TUNE_BUCKET_SORTBACK: g_bucket_sortback.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -14,28 +14,32 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "readme_example.json")
 
 
-@pytest.fixture(scope="module", params=["reorder_always", "reorder_never", "defaults", "no_ext_table"])
+@pytest.fixture(scope="module", params=["reorder_always", "reorder_never", "defaults", "no_ext_table", "radix_sortback"])
 def fm(request):
     """Every parity test runs with the batch reordering (sweep search for fixed-length batches, locality sort for the
     rest) forced on, forced off (and the kernels reading the blob's occ sections in place instead of the interleaved
     copy), at its default thresholds, and without the extended k-mer table (so that long patterns seed from the blob's
-    own kLTS): results must not depend on any of it."""
+    own kLTS), and with the reordered batches radix-sorted back into the caller's order instead of the bucketed sort-back:
+    results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
     L = _ffi.lib()
     never = 2**64 - 1
-    sort_min, sweep_min, ext_bits, ilv = {"reorder_always": (0, 0, 24, 1), "reorder_never": (never, never, 24, 0),
-                                          "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1),
-                                          "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1)}[request.param]
+    sort_min, sweep_min, ext_bits, ilv, bucket = {
+        "reorder_always": (0, 0, 24, 1, 1), "reorder_never": (never, never, 24, 0, 1),
+        "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1, 1),
+        "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1, 1), "radix_sortback": (0, 0, 24, 1, 0)}[request.param]
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, ext_bits) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, 1)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
