@@ -60,8 +60,8 @@ extern "C" {
     pub fn svfm_count_batch(ix: *mut svfm_index, pats: *const u8, offs: *const u64, n: u64, fixed_len: u32,
                             flags: u32, counts_out: *mut c_void) -> c_int;
     pub fn svfm_locate_batch_alloc(ix: *mut svfm_index, pats: *const u8, offs: *const u64, n: u64, fixed_len: u32,
-                                   flags: u32, out_offs: *mut u64, positions: *mut *mut c_void,
-                                   total: *mut u64) -> c_int;
+                                   flags: u32, out_offs: *mut c_void /* u64[n+1]; u32[n+1] with SVFM_OFFS32 */,
+                                   positions: *mut *mut c_void, total: *mut u64) -> c_int;
     pub fn svfm_free_positions(positions: *mut c_void);
     pub fn svfm_last_error() -> *const c_char;
     // the rest of include/svfm.h
@@ -71,7 +71,13 @@ extern "C" {
     pub fn svfm_index_info(ix: *const svfm_index, out: *mut svfm_info) -> c_int;
     pub fn svfm_index_memory(ix: *mut svfm_index, out: *mut u64) -> c_int; // [4]: blob, ext table, interleaved occ, scratch
     pub fn svfm_locate_batch(ix: *mut svfm_index, pats: *const u8, offs: *const u64, n: u64, fixed_len: u32, flags: u32,
-                             out_offs: *mut u64, positions: *mut c_void, capacity: u64, total: *mut u64) -> c_int;
+                             out_offs: *mut c_void, positions: *mut c_void, capacity: u64, total: *mut u64) -> c_int;
+    // packed fixed-length batches: ceil(len*bits/8) bytes per pattern, symbol indices, first symbol in the lowest bits
+    pub fn svfm_count_batch_packed(ix: *mut svfm_index, packed: *const u8, n: u64, len: u32, bits: u32, flags: u32,
+                                   counts_out: *mut c_void) -> c_int;
+    pub fn svfm_locate_batch_packed(ix: *mut svfm_index, packed: *const u8, n: u64, len: u32, bits: u32, flags: u32,
+                                    out_offs: *mut c_void, positions: *mut c_void, capacity: u64, total: *mut u64) -> c_int;
+    pub fn svfm_pack_patterns(pats: *const u8, n: u64, len: u32, table256: *const u8, bits: u32, packed_out: *mut u8) -> c_int;
     pub fn svfm_count(ix: *mut svfm_index, pattern: *const u8, len: u64, flags: u32, count: *mut u64) -> c_int;
     pub fn svfm_locate(ix: *mut svfm_index, pattern: *const u8, len: u64, flags: u32, positions: *mut c_void,
                        capacity: u64, total: *mut u64) -> c_int;

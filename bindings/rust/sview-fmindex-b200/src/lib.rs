@@ -58,8 +58,10 @@ impl<'a, P: Position, B: GpuBlock, E: GpuEncoder> GpuFmIndex<'a, P, B, E> {
         let mut out_offs = vec![0u64; patterns.len() + 1];
         let (mut pos, mut total) = (core::ptr::null_mut(), 0u64);
         let rc = unsafe { sys::svfm_locate_batch_alloc(self.handle, data.as_ptr(), offs.as_ptr(), patterns.len() as u64, 0,
-                                                       flags, out_offs.as_mut_ptr(), &mut pos, &mut total) };
+                                                       flags, out_offs.as_mut_ptr() as *mut _, &mut pos, &mut total) };
         assert!(rc == sys::SVFM_OK, "svfm_locate_batch: {rc}");
+        // no occurrence at all: the library returns a null pointer, which slice::from_raw_parts must never see
+        if total == 0 || pos.is_null() { return (out_offs, Vec::new()); }
         let v = unsafe { core::slice::from_raw_parts(pos as *const P, total as usize) }.to_vec();
         unsafe { sys::svfm_free_positions(pos) };
         (out_offs, v)

@@ -120,14 +120,29 @@ int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, 
  * positions[out_offs[i] .. out_offs[i+1]).  If *total > capacity nothing is written to `positions`,
  * out_offs and *total are still valid and the call returns SVFM_ERR_CAPACITY. */
 int svfm_locate_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n,
-                      uint32_t fixed_len, uint32_t flags, uint64_t* out_offs, void* positions,
-                      uint64_t capacity, uint64_t* total);
+                      uint32_t fixed_len, uint32_t flags, void* out_offs /* u64[n+1]; u32[n+1] with SVFM_OFFS32 */,
+                      void* positions, uint64_t capacity, uint64_t* total);
 /* Same, positions allocated by the library (like the Vec<P> `locate` returns; pinned host memory for results of
  * 1 MiB and more, plain memory below); release with svfm_free_positions only. */
 int svfm_locate_batch_alloc(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n,
-                            uint32_t fixed_len, uint32_t flags, uint64_t* out_offs, void** positions,
+                            uint32_t fixed_len, uint32_t flags, void* out_offs, void** positions,
                             uint64_t* total);
 void svfm_free_positions(void* positions);
+
+/* ---- packed fixed-length batches (fewer bytes over PCIe; the calls above stay the drop-in ones) -----------------
+ * Pattern i occupies bytes [i*bpp, (i+1)*bpp) of `packed`, bpp = ceil(len*bits/8); symbol j of the pattern (the value
+ * `TextEncoder::idx_of` returns for its byte, encoding_table.rs:9-11) sits in bits [j*bits, (j+1)*bits) of that little-
+ * endian bit string; bits in 1..8 and every symbol index < 2^bits (so 2 bits carry ACGT even when the table also has an
+ * N class; a pattern with a symbol index >= symbol_count fails with SVFM_ERR_BAD_SYMBOL).  20 bp at 2 bits = 5 bytes
+ * instead of 20.  Results are those of the unpacked calls on the same patterns.  SVFM_REVERSED is not supported.
+ * svfm_pack_patterns is a multi-threaded host helper producing this layout from byte patterns (table256 = the
+ * EncodingTable bytes, NULL = bytes are symbol indices already); SVFM_ERR_BAD_SYMBOL when a symbol does not fit `bits`. */
+int svfm_count_batch_packed(svfm_index* ix, const uint8_t* packed, uint64_t n, uint32_t len, uint32_t bits,
+                            uint32_t flags, void* counts_out);
+int svfm_locate_batch_packed(svfm_index* ix, const uint8_t* packed, uint64_t n, uint32_t len, uint32_t bits,
+                             uint32_t flags, void* out_offs, void* positions, uint64_t capacity, uint64_t* total);
+int svfm_pack_patterns(const uint8_t* pats, uint64_t n, uint32_t len, const uint8_t* table256, uint32_t bits,
+                       uint8_t* packed_out);
 
 /* Single-pattern conveniences = the batch calls with n = 1.
  * `count(&self, pattern:&[u8]) -> P`, `locate_to_buffer(&self, pattern, &mut Vec<P>)` (appends). */

@@ -1,6 +1,6 @@
 /*
- * svfm_bench.h -- measurement and self-check helpers exported by libsvfm.so next to the product ABI
- * (include/svfm.h).  Not part of the reference's interface: synthetic data generation on the device
+ * svfm_bench.h -- measurement and self-check helpers, exported by libsvfm_bench.so (NOT by the product library
+ * libsvfm.so, whose ABI is include/svfm.h).  Not part of the reference's interface: synthetic data generation on the device
  * (bench.py builds 1-3 Gbp indexes inside one GPU job), the random-32-byte-sector gather microbenchmark
  * that defines the roofline of SURVEY.md section 8d, and size-independent result checks.
  * All pointers named d_* are device pointers on the current device; everything runs on `stream`
@@ -51,6 +51,9 @@ int svfm_bench_count_digest(const void* d_counts, uint32_t pos_bits, uint64_t n,
 
 /* Write `bytes` of d_buf (flushes L2 when bytes > L2 size). */
 int svfm_bench_flush_l2(uint8_t* d_buf, uint64_t bytes, void* stream);
+
+/* thread-local text of the last failure inside this library */
+const char* svfm_bench_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVFM_LIB_PATH") or os.path.join(_HERE, "libsvfm.so")  # override: developer builds only
+BENCH_LIB_PATH = os.path.join(_HERE, "libsvfm_bench.so")  # include/svfm_bench.h: measurement helpers, not the product
 
 SVFM_OK = 0
 SVFM_ERR_INVALID_FORMAT = 1
@@ -69,6 +70,9 @@ EXPORTS = [
     ("svfm_locate_batch", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint64, _u64p]),
     ("svfm_locate_batch_alloc", C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, C.POINTER(_vp), _u64p]),
     ("svfm_free_positions", None, [_vp]),
+    ("svfm_count_batch_packed", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    ("svfm_locate_batch_packed", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint64, _u64p]),
+    ("svfm_pack_patterns", C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp, C.c_uint32, _vp]),
     ("svfm_count", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, _u64p]),
     ("svfm_locate", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32, _vp, C.c_uint64, _u64p]),
     ("svfm_session_create", C.c_int, [_vp, C.POINTER(_vp)]),
@@ -100,12 +104,40 @@ BENCH_EXPORTS = [
                                            _vp, _u64p, _u64p, _vp]),
     ("svfm_bench_count_digest", C.c_int, [_vp, C.c_uint32, C.c_uint64, _u64p, _u64p, _vp]),
     ("svfm_bench_flush_l2", C.c_int, [_vp, C.c_uint64, _vp]),
+    ("svfm_bench_last_error", C.c_char_p, []),
 ]
 
 _lib = None
+_bench = None
 
 
-def lib() -> C.CDLL:
+class _Libs:
+    """The product library, plus -- loaded on first use of a svfm_bench_* name -- the measurement helpers."""
+
+    def __init__(self, product):
+        self._product = product
+
+    def __getattr__(self, name):
+        if name.startswith("svfm_bench_"):
+            return getattr(bench_lib(), name)
+        return getattr(self._product, name)
+
+
+def bench_lib() -> C.CDLL:
+    global _bench
+    if _bench is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise ImportError(f"{BENCH_LIB_PATH} is missing: build it with `make -C sview_fmindex_b200/csrc`")
+        B = C.CDLL(BENCH_LIB_PATH)
+        for name, restype, argtypes in BENCH_EXPORTS:
+            fn = getattr(B, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _bench = B
+    return _bench
+
+
+def lib() -> _Libs:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
@@ -113,9 +145,9 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C sview_fmindex_b200/csrc` (there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
-        for name, restype, argtypes in EXPORTS + BENCH_EXPORTS:
+        for name, restype, argtypes in EXPORTS:
             fn = getattr(L, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        _lib = L
+        _lib = _Libs(L)
     return _lib

@@ -5,7 +5,7 @@ its `run_benchmark.sh` can be reproduced end to end and results diffed line by l
     python -m sview_fmindex_b200.bench_cli generate-text    -d DIR -t 1000000000 -s 42
     python -m sview_fmindex_b200.bench_cli generate-pattern -d DIR -p 20 -n 100000 -s 42
     python -m sview_fmindex_b200.bench_cli build  -d DIR -s 2 -k 3 [-t]      # text.txt -> sview-memory-block{3,2}.blob
-    python -m sview_fmindex_b200.bench_cli locate -d DIR [-t]                  # pattern.txt -> <stem>-results.txt
+    python -m sview_fmindex_b200.bench_cli locate -d DIR [-t] [-a sview-mmap]  # pattern.txt -> <stem>-results.txt
 
   * blob file names, symbols (`Aa,Cc,Gg,Tt[,Nn]`, `bench/src/build/mod.rs:28-30`), Block2<u64> with `-t` / Block3<u64>
     without, u32 positions, SASR / KLTS meaning: `bench/src/build/sview_memory.rs:10-107`.  The blob is the reference's
@@ -14,6 +14,10 @@ its `run_benchmark.sh` can be reproduced end to end and results diffed line by l
   * `locate` reads `pattern.txt` (one pattern per line), runs ONE `locate_batch` over all lines instead of one `locate`
     call per line (`bench/src/locate/sview_memory.rs:32-36`), and writes one line per pattern: positions in the reference's
     SA-row order joined by "," (`bench/src/locate/mod.rs:115-123`); absent patterns give an empty line.
+  * `locate -a sview-mmap` maps the blob file instead of reading it (`bench/src/locate/sview_mmap.rs:20-46`: `Mmap::map` +
+    the optional MMAP_ADVICE_RANDOM / MMAP_ADVICE_SEQUENTIAL / MMAP_ADVICE_DONTDUMP advice, same environment variables) and
+    hands the mapping to `FmIndex::load`, which uploads straight out of the page cache; `-a sview-memory` (default) reads
+    the file into memory first (`bench/src/locate/sview_memory.rs:19`).
   * `generate-*` use this repo's counter-based generator (sview_fmindex_b200/synth.py), not Rust's `StdRng`, so the bytes
     differ from the reference's for the same seed; shapes and formats are the same (`bench/src/generate.rs:37-45,105-114`).
 The timing lines keep the reference's wording ("Blob loading time", "Locate processing time", ...; nanoseconds)."""
@@ -128,6 +132,24 @@ def cmd_build(a):
     return 0
 
 
+def map_blob(path: str) -> np.ndarray:
+    """bench/src/locate/sview_mmap.rs:20-46: read-only mapping of the blob file + the advice the environment asks for."""
+    import mmap
+    m = np.memmap(path, dtype=np.uint8, mode="r")
+    raw = getattr(m, "_mmap", None)
+    if raw is not None and hasattr(raw, "madvise"):
+        if "MMAP_ADVICE_RANDOM" in os.environ:
+            print("Applying MADV_RANDOM advice to mmap")
+            raw.madvise(mmap.MADV_RANDOM)
+        elif "MMAP_ADVICE_SEQUENTIAL" in os.environ:
+            print("Applying MADV_SEQUENTIAL advice to mmap")
+            raw.madvise(mmap.MADV_SEQUENTIAL)
+        elif "MMAP_ADVICE_DONTDUMP" in os.environ and hasattr(mmap, "MADV_DONTDUMP"):
+            print("Applying MADV_DONTDUMP advice to mmap")
+            raw.madvise(mmap.MADV_DONTDUMP)
+    return m
+
+
 def cmd_locate(a):
     from . import FmIndex
     t_total = time.perf_counter_ns()
@@ -138,7 +160,10 @@ def cmd_locate(a):
         return 1
     print(f"Using blob file: {blob_path}")
     t0 = time.perf_counter_ns()
-    blob = np.fromfile(blob_path, dtype=np.uint8)
+    if a.algorithm == "sview-mmap":
+        blob = map_blob(blob_path)
+    else:
+        blob = np.fromfile(blob_path, dtype=np.uint8)
     ix = FmIndex.load(blob, index_type(a.treat_t_as_wildcard), device=a.device)
     load_ns = time.perf_counter_ns() - t0
     t0 = time.perf_counter_ns()
@@ -188,6 +213,8 @@ def main(argv=None) -> int:
     g = sub.add_parser("locate")
     g.add_argument("-d", "--data-dir", default="test_data")
     g.add_argument("-t", "--treat-t-as-wildcard", action="store_true")
+    g.add_argument("-a", "--algorithm", default="sview-memory", choices=["sview-memory", "sview-mmap"],
+                   help="how the blob is loaded (bench/src/locate/mod.rs:44-45)")
     g.add_argument("--device", type=int, default=0)
     g.set_defaults(fn=cmd_locate)
     a = ap.parse_args(argv)

@@ -1,8 +1,11 @@
-// benchtools.cu -- measurement / self-check helpers (include/svfm_bench.h).  Not part of the product path.
+// benchtools.cu -- measurement / self-check helpers (include/svfm_bench.h).  Not part of the product path: built into its
+// own library, libsvfm_bench.so, which shares nothing with libsvfm.so but device pointers passed through the caller.
 #include "common.cuh"
 #include "../../include/svfm_bench.h"
 
 namespace svfm {
+thread_local std::string g_last_error;   // this library's own copies (common.cuh declares them)
+std::atomic<uint64_t> g_launches{0};
 namespace {
 
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
@@ -230,3 +233,5 @@ int svfm_bench_flush_l2(uint8_t* d_buf, uint64_t bytes, void* stream) {
 }
 
 }  // extern "C"
+
+extern "C" const char* svfm_bench_last_error(void) { return svfm::g_last_error.c_str(); }

@@ -87,9 +87,19 @@ inline int builder_layout(const svfm_type& t, uint64_t text_len, uint32_t symbol
     L.kmer_size = kmer_size;
     L.count_array_len = symbol_count + 1;
     L.kmer_multiplier_len = kmer_size;
-    uint32_t p = 1;  // u32 pow, as in count_array.rs:70
-    for (uint32_t e = 0; e < kmer_size; e++) p *= (symbol_count + 1);
-    L.kmer_count_table_len = p;
+    // (S+1)^k: the reference computes it with u32::pow (count_array.rs:70), which panics on overflow in debug builds and
+    // wraps in release builds (the table is then too short for the indices the search computes, and the reference panics
+    // on the bounds check).  Neither is acceptable across a C ABI, and the device histogram is indexed with the true
+    // value: anything that does not fit the reference's u32 is an invalid configuration.
+    unsigned __int128 p = 1;
+    for (uint32_t e = 0; e < kmer_size; e++) {
+        p *= (symbol_count + 1);
+        if (p > (unsigned __int128)0xffffffffu) {
+            if (detail) { detail[0] = 0xffffffffu; detail[1] = kmer_size; }
+            return SVFM_ERR_INVALID_CONFIG;
+        }
+    }
+    L.kmer_count_table_len = (uint64_t)p;
     L.sampling_ratio = sampling_ratio;
     L.suffix_array_len = text_len / sampling_ratio + (text_len % sampling_ratio ? 1 : 0);
     L.blocks_len = text_len / t.vec_bits + 1;

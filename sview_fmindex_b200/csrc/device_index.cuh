@@ -97,7 +97,8 @@ struct Block {
     // measured slower once the sweep search made neighbouring lanes share blocks (round 1: 14.17 -> 13.64 ms of
     // sweep_round_kernel time per 10^8 patterns).  Even word counts (Block2/4/6<u64>, u128 vectors) load 16 bytes at a time:
     // the blocks section is shifted onto a 32-byte boundary at load (svfm_load).
-    __device__ __forceinline__ void load(const void* blocks, uint64_t q) {
+    template <class Q>
+    __device__ __forceinline__ void load(const void* blocks, Q q) {
         constexpr int NW = NPL * T::WORDS;
         if constexpr (sizeof(W) == 8 && (NW & 1)) {
             const unsigned long long* base = reinterpret_cast<const unsigned long long*>(blocks) + q * (uint64_t)NW;
@@ -165,6 +166,21 @@ struct Block {
         }
     }
 
+    // The same in two halves, so that several blocks share the per-symbol part: flip[v] = all ones where plane v must be 0.
+    __device__ __forceinline__ static void flips(uint32_t symidx, W (&flip)[NPL]) {
+#pragma unroll
+        for (int v = 0; v < NPL; v++) flip[v] = ((symidx >> v) & 1u) ? (W)0 : ~(W)0;
+    }
+    __device__ __forceinline__ void match_flips(const W (&flip)[NPL], W (&m)[T::WORDS]) const {
+#pragma unroll
+        for (int k = 0; k < T::WORDS; k++) m[k] = w[0][k] ^ flip[0];
+#pragma unroll
+        for (int v = 1; v < NPL; v++) {
+#pragma unroll
+            for (int k = 0; k < T::WORDS; k++) m[k] &= (w[v][k] ^ flip[v]);
+        }
+    }
+
     // popcount of the first `rem` symbols of a match mask; rem in [0, VBITS) (0 -> 0).
     __device__ __forceinline__ static uint32_t prefix_count(const W (&m)[T::WORDS], uint32_t rem) {
         if (T::WORDS == 1) {
@@ -198,12 +214,16 @@ struct Block {
     }
 };
 
+// Block numbers: 32 bits for 32-bit positions, 64 bits otherwise (offsets derived from them are computed in 64 bits).
+template <class P> struct QuotientOf { using type = uint64_t; };
+template <> struct QuotientOf<uint32_t> { using type = uint32_t; };
+
 // BwmView::get_next_rank (components/bwm/mod.rs:197-215) split in two so that the caller can issue
 // the loads of several ranks before consuming any of them.
-template <class P, int VBITS>
-__device__ __forceinline__ void rank_addr(const DevIndex<P>& ix, P pos, uint64_t& q, uint32_t& rem) {
+template <class P, int VBITS, class Q>
+__device__ __forceinline__ void rank_addr(const DevIndex<P>& ix, P pos, Q& q, uint32_t& rem) {
     if (pos < ix.sentinel_index) pos += 1;                  // bwm/mod.rs:202-204
-    q = (uint64_t)pos >> VecTraits<VBITS>::LOG2;            // div_rem_with_u32(BLOCK_LEN), text_length.rs:78
+    q = (Q)(pos >> VecTraits<VBITS>::LOG2);                 // div_rem_with_u32(BLOCK_LEN), text_length.rs:78
     rem = (uint32_t)pos & (uint32_t)(VBITS - 1);
 }
 

@@ -56,7 +56,7 @@ struct svfm_uploader {
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
-    svfm::DeviceBuffer pats, offs, sp, cnt, counts_out, woffs, out_offs, offs64, positions, positions_alt, cub_temp;
+    svfm::DeviceBuffer pats, offs, unpacked, sp, cnt, counts_out, woffs, out_offs, offs64, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
     svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // radix sort-back of (pattern index -> position) records (SVFM_SORTED)
@@ -231,10 +231,19 @@ static int run_build_ext(svfm_index* ix, uint64_t ext_bits) {
     if (entries > 0xfffffff0ull) return SVFM_OK;
     DevIndex<P> dix = make_dev_index<P>(ix);
     P *a = nullptr, *b = nullptr;
-    SVFM_CUDA(cudaMalloc(&a, entries * 2 * sizeof(P)));
-    if (m > 1) {
-        cudaError_t e = cudaMalloc(&b, entries / s_eff * 2 * sizeof(P));
-        if (e != cudaSuccess) { cudaFree(a); SVFM_CUDA(e); }
+    // The table is optional (the search kernels fall back to the blob's own k-mer table): when the allocation fails --
+    // another load on the same GPU may have taken the memory since cudaMemGetInfo -- retry with 2^24 entries, then go without.
+    for (;;) {
+        cudaError_t e = cudaMalloc(&a, entries * 2 * sizeof(P));
+        if (e == cudaSuccess && m > 1) {
+            e = cudaMalloc(&b, entries / s_eff * 2 * sizeof(P));
+            if (e != cudaSuccess) { cudaFree(a); a = nullptr; }
+        }
+        if (e == cudaSuccess) break;
+        (void)cudaGetLastError();
+        if (e != cudaErrorMemoryAllocation) SVFM_CUDA(e);
+        if (entries <= (1ull << 24)) return SVFM_OK;  // no table
+        while (entries > (1ull << 24) && m > 1) { entries /= s_eff; m--; }
     }
     // levels alternate between the two buffers so that level m lands in `a`
     P* cur = (m % 2 == 1) ? a : b;

@@ -15,7 +15,34 @@ struct PatternBatch {
     uint64_t n;
     uint32_t fixed_len;
     uint32_t reversed;     // patterns stored back-to-front (rev-iter twins, locate/with_rev_iter.rs)
+    uint32_t preencoded;   // bytes are symbol indices already (packed entry points): the encoding table is skipped
 };
+
+// Packed fixed-length patterns (svfm_*_batch_packed): symbol indices, `bits` bits each, first symbol in the lowest bits
+// of the first byte, every pattern padded to a whole number of bytes (bpp).  Expands them to one byte per symbol.
+static __global__ void __launch_bounds__(256)
+unpack_patterns_kernel(const uint8_t* __restrict__ packed, uint64_t n, uint32_t len, uint32_t bits, uint32_t bpp,
+                       uint8_t* __restrict__ out) {
+    const uint64_t total = n * (uint64_t)len;
+    const uint32_t mask = (1u << bits) - 1u;
+    // one thread produces 4 consecutive output bytes (the output buffer is padded to a multiple of 4)
+    for (uint64_t o = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; o < total; o += (uint64_t)gridDim.x * blockDim.x * 4) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint64_t at = o + b;
+            if (at < total) {
+                const uint64_t i = at / len;
+                const uint32_t bit = (uint32_t)(at - i * len) * bits;
+                const uint8_t* p = packed + i * (uint64_t)bpp + (bit >> 3);
+                uint32_t v = p[0];
+                if ((bit & 7u) + bits > 8u) v |= (uint32_t)p[1] << 8;   // bits <= 8: a symbol spans at most two bytes
+                word |= ((v >> (bit & 7u)) & mask) << (8 * b);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(out + o) = word;
+    }
+}
 
 constexpr int SEARCH_THREADS = 256;
 constexpr uint32_t HEAVY_ROWS = 1024;  // patterns with more SA rows than this are located row-parallel
@@ -29,54 +56,49 @@ struct SbOut {
 };
 
 // One backward-search step for both range ends: FmIndex::next_pos_range (locate/mod.rs:39-45) =
-// count_array[s] + get_next_rank(pos, s) (bwm/mod.rs:197-215) for pos in {sp, ep}.
-// All four gathers (2 checkpoint words + 2 blocks) are issued before the first use; when both ends
-// fall into the same block (the common case once the interval is short) the block and the
-// checkpoint word are fetched once.
+// count_array[s] + get_next_rank(pos, s) (bwm/mod.rs:197-215) for pos in {sp, ep}; c = count_array[sym].
+// Straight-line code: the block and checkpoint word of sp are always fetched, those of ep only when ep falls into another
+// block (predicated loads); the match mask and prefix popcount then run for both ends unconditionally.  The round-1
+// version branched into a one-block and a two-block path; inside a warp some lane almost always needs the second block
+// (a 4-row interval straddles a 64-row block boundary with probability 1/16, so 86 % of all warps), and every warp then
+// executed both paths: 98 instructions per warp and step, against ~60 here (ncu source view, sweep_round_kernel).
 template <class P, int NPL, int VBITS, bool ILV = false>
-__device__ __forceinline__ void backward_step(const DevIndex<P>& ix, const P* __restrict__ s_count, uint32_t sym,
-                                              P& sp, P& ep) {
-    uint64_t q0, q1;
+__device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sym, P c, P& sp, P& ep) {
+    using B = Block<NPL, VBITS>;
+    using Q = typename QuotientOf<P>::type;   // block number: 32 bits are enough for 32-bit positions (compares, moves)
+    Q q0, q1;
     uint32_t r0, r1;
     rank_addr<P, VBITS>(ix, sp, q0, r0);
     rank_addr<P, VBITS>(ix, ep, q1, r1);
-    const P c = s_count[sym];
-    Block<NPL, VBITS> b0;
-    typename Block<NPL, VBITS>::W m[VecTraits<VBITS>::WORDS];
-    if (q0 == q1) {
-        P ck;
-        if constexpr (ILV) {
-            const uint8_t* e0 = ix.ilv + q0 * ix.ilv_stride;
-            ck = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
-            b0.load_aligned(e0);
-        } else {
-            ck = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
-            b0.load(ix.blocks, q0);
-        }
-        b0.match_mask(sym, m);
-        sp = c + ck + (P)Block<NPL, VBITS>::prefix_count(m, r0);
-        ep = c + ck + (P)Block<NPL, VBITS>::prefix_count(m, r1);
+    B b0, b1;
+    P ck0, ck1;
+    if constexpr (ILV) {
+        const uint8_t* e0 = ix.ilv + (uint64_t)q0 * ix.ilv_stride;
+        ck0 = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
+        b0.load_aligned(e0);
     } else {
-        Block<NPL, VBITS> b1;
-        P ck0, ck1;
+        ck0 = ld_gather<P>(ix.rank_checkpoints + ((uint64_t)q0 * ix.symbol_count + sym));
+        b0.load(ix.blocks, q0);
+    }
+    b1 = b0;
+    ck1 = ck0;
+    if (q1 != q0) {
         if constexpr (ILV) {
-            const uint8_t* e0 = ix.ilv + q0 * ix.ilv_stride;
-            const uint8_t* e1 = ix.ilv + q1 * ix.ilv_stride;
-            ck0 = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
+            const uint8_t* e1 = ix.ilv + (uint64_t)q1 * ix.ilv_stride;
             ck1 = ld_gather<P>(reinterpret_cast<const P*>(e1 + ix.ilv_ck_off) + sym);
-            b0.load_aligned(e0);
             b1.load_aligned(e1);
         } else {
-            ck0 = ld_gather<P>(ix.rank_checkpoints + q0 * ix.symbol_count + sym);
-            ck1 = ld_gather<P>(ix.rank_checkpoints + q1 * ix.symbol_count + sym);
-            b0.load(ix.blocks, q0);
+            ck1 = ld_gather<P>(ix.rank_checkpoints + ((uint64_t)q1 * ix.symbol_count + sym));
             b1.load(ix.blocks, q1);
         }
-        b0.match_mask(sym, m);
-        sp = c + ck0 + (P)Block<NPL, VBITS>::prefix_count(m, r0);
-        b1.match_mask(sym, m);
-        ep = c + ck1 + (P)Block<NPL, VBITS>::prefix_count(m, r1);
     }
+    typename B::W flip[NPL];
+    B::flips(sym, flip);
+    typename B::W m[VecTraits<VBITS>::WORDS];
+    b0.match_flips(flip, m);
+    sp = (P)(c + ck0 + (P)B::prefix_count(m, r0));
+    b1.match_flips(flip, m);
+    ep = (P)(c + ck1 + (P)B::prefix_count(m, r1));
 }
 
 // Locality key of a pattern = its trailing symbols packed `bits` per symbol from the top of a u64, the
@@ -88,7 +110,7 @@ static __global__ void __launch_bounds__(SEARCH_THREADS)
 pack_keys_kernel(const uint8_t* __restrict__ table, uint32_t S, const PatternBatch pb, uint32_t bits,
                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ err) {
     __shared__ uint8_t s_table[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = table ? table[i] : (uint8_t)i;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = (table && !pb.preencoded) ? table[i] : (uint8_t)i;
     __syncthreads();
     const uint32_t m = 64u / bits;
     int errbits = 0;
@@ -136,7 +158,7 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
     __shared__ uint8_t s_table[256];
     __shared__ uint8_t s_rank[64];
     __shared__ P s_count[65];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = ix.table ? ix.table[i] : (uint8_t)i;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = (ix.table && !pb.preencoded) ? ix.table[i] : (uint8_t)i;
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = ix.sym_rank[i];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     __syncthreads();
@@ -202,7 +224,7 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io)
             // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
             while (sp < ep && pi > 0) {
                 pi -= 1;
-                backward_step<P, NPL, VBITS, ILV>(ix, s_count, sym_at(pi), sp, ep);
+                { const uint32_t sy = sym_at(pi); backward_step<P, NPL, VBITS, ILV>(ix, sy, s_count[sy], sp, ep); }
             }
         }
         const P cnt = (P)(ep - sp);
@@ -266,7 +288,7 @@ ext_expand_kernel(const DevIndex<P> ix, const P* __restrict__ in, uint64_t n_in,
         const uint64_t c = t / n_in, i = t - c * n_in;
         P sp = in[2 * i];
         P ep = (P)(sp + in[2 * i + 1]);
-        if (sp < ep) backward_step<P, NPL, VBITS>(ix, s_count, ix.present[c], sp, ep);
+        if (sp < ep) { const uint32_t sy = ix.present[c]; backward_step<P, NPL, VBITS>(ix, sy, s_count[sy], sp, ep); }
         out[2 * t] = sp;
         out[2 * t + 1] = (P)(ep - sp);
     }
@@ -334,7 +356,7 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     const uint32_t nb = 1u << digit_bits;
     for (uint32_t i = threadIdx.x; i < n_rounds * nb; i += blockDim.x) s_hist[i] = 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t sidx = table ? table[i] : (uint32_t)i;
+        uint32_t sidx = (table && !pb.preencoded) ? table[i] : (uint32_t)i;
         const uint32_t bad = sidx >= S ? 0x8000u : 0u;     // PassThrough byte >= S
         if (sidx >= S) sidx = S - 1;
         s_lut[i] = (uint16_t)(sidx | ((uint32_t)(syms.sym_rank[sidx] & 0x7fu) << 8) | (syms.sym_rank[sidx] == 0xffu ? 0x4000u : 0u) | bad);
@@ -442,7 +464,10 @@ struct alignas((2 * sizeof(P) + sizeof(R) + 4) % 16 == 0 ? 16 : 8) SweepItem {
     uint32_t idx;
 };
 
-constexpr int ROUND_THREADS = 256;
+#ifndef SVFM_ROUND_THREADS
+#define SVFM_ROUND_THREADS 256
+#endif
+constexpr int ROUND_THREADS = SVFM_ROUND_THREADS;
 #ifndef SVFM_ROUND_ITEMS
 #define SVFM_ROUND_ITEMS 4
 #endif
@@ -651,8 +676,11 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         for (int k = 0; k < ROUND_ITEMS; k++) {
             if (cnt[k] != 0) {
                 P ep = (P)(sp[k] + cnt[k]);
-                for (uint32_t t = 0; t < steps && sp[k] < ep; t++)
-                    backward_step<P, NPL, VBITS>(ix, s_count, s_present[(uint32_t)((rest[k] >> (shift + bits * t)) & sym_mask)], sp[k], ep);
+                R left = (R)(rest[k] >> shift);
+                for (uint32_t t = 0; t < steps && sp[k] < ep; t++, left >>= bits) {
+                    const uint32_t sy = s_present[(uint32_t)(left & sym_mask)];
+                    backward_step<P, NPL, VBITS>(ix, sy, s_count[sy], sp[k], ep);
+                }
                 cnt[k] = (P)(ep - sp[k]);
             }
             if (io.heavy_seen && (uint64_t)cnt[k] > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);

@@ -1,6 +1,7 @@
 // svfm_api.cu -- C ABI (include/svfm.h) of the B200-native batched FM-index search engine.
 // Index handle, sessions (stream + scratch arena), host/device batch entry points.
 // Citations are relative to the reference's sview-fmindex/src/.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -126,6 +127,7 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
 // ---------------------------------------------------------------------------------------------
 // sessions
 // ---------------------------------------------------------------------------------------------
+static void session_delete(svfm_session* s);
 static int session_new(svfm_index* ix, svfm_session** out) {
     SVFM_CUDA(cudaSetDevice(ix->device));
     svfm_session* s = new svfm_session();
@@ -136,8 +138,9 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(uint64_t), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         g_last_error = std::string("session_new: ") + cudaGetErrorString(e);
-        delete s;
-        return SVFM_ERR_CUDA;
+        (void)cudaGetLastError();
+        session_delete(s);  // frees whatever was created before the failure (every member is null-checked)
+        return e == cudaErrorMemoryAllocation ? SVFM_ERR_NOMEM : SVFM_ERR_CUDA;
     }
     *out = s;
     return SVFM_OK;
@@ -712,7 +715,8 @@ static void result_free(void* p) {
     if (h->pinned) cudaFreeHost(h); else std::free(h);
 }
 
-__global__ void add_base_kernel(uint64_t* __restrict__ v, uint64_t n, uint64_t base) {
+template <class T>
+__global__ void add_base_kernel(T* __restrict__ v, uint64_t n, T base) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] += base;
 }
 
@@ -840,6 +844,7 @@ static int await_chunk(svfm_session* s, const ChunkPlan& cp, UploadGroup& g, uin
     pb.n = b - a;
     pb.fixed_len = g.fixed_len;
     pb.reversed = (g.flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.preencoded = 0;
     if (!g.offs) {
         pb.pats = (const uint8_t*)g.u->pats.ptr + (a - g.first_pattern) * (uint64_t)g.fixed_len;
         pb.offs = nullptr;
@@ -935,6 +940,7 @@ static int upload_direct(svfm_session* s, const uint8_t* pats, const uint64_t* o
     pb.n = n;
     pb.fixed_len = fixed_len;
     pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.preencoded = 0;
     pb.offs = nullptr;
     const uint64_t bytes = offs ? offs[n] - offs[0] : n * (uint64_t)fixed_len;
     if ((rc = s->pats.reserve(bytes + 256))) return rc;
@@ -948,8 +954,29 @@ static int upload_direct(svfm_session* s, const uint8_t* pats, const uint64_t* o
     return SVFM_OK;
 }
 
+// Packed entry points: the host buffer holds `bpp` bytes per pattern (what the upload machinery sees as fixed_len); each
+// chunk is expanded on the device to one symbol index per byte before the usual pipeline runs on it.
+struct PackedSpec {
+    uint32_t bits = 0;  // 0: not packed
+    uint32_t len = 0;   // symbols per pattern
+};
+static int unpack_chunk(svfm_session* s, const PackedSpec& spec, PatternBatch& pb) {
+    if (!spec.bits) return SVFM_OK;
+    const uint64_t bytes = pb.n * (uint64_t)spec.len;
+    int rc;
+    if ((rc = s->unpacked.reserve(bytes + 256))) return rc;
+    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 1);
+    unpack_patterns_kernel<<<grid_for((bytes + 3) / 4, 256, s->ix->device), 256, 0, s->stream>>>(pb.pats, pb.n, spec.len, spec.bits, pb.fixed_len,
+                                                                                             (uint8_t*)s->unpacked.ptr);
+    SVFM_CUDA(cudaGetLastError());
+    pb.pats = (const uint8_t*)s->unpacked.ptr;
+    pb.fixed_len = spec.len;
+    pb.preencoded = 1;
+    return SVFM_OK;
+}
+
 static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                      uint32_t flags, void* counts_out) {
+                      uint32_t flags, void* counts_out, const PackedSpec& spec = PackedSpec()) {
     const uint64_t P = ix->type.pos_bits / 8;
     const ChunkPlan cp = plan_chunks(n);
     if (cp.chunks == 1) {
@@ -959,6 +986,7 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
         svfm_session* s = lease.s;
         PatternBatch pb;
         if ((r = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return r;
+        if ((r = unpack_chunk(s, spec, pb))) return r;
         if ((r = s->counts_out.reserve(n * P))) return r;
         if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
         SVFM_CUDA(cudaMemcpyAsync(counts_out, s->counts_out.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
@@ -978,6 +1006,7 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
             PatternBatch pb;
             int r;
             if ((r = await_chunk(s, cp, g, c, pb))) return r;
+            if ((r = unpack_chunk(s, spec, pb))) return r;
             if ((r = s->counts_out.reserve((b - a) * P))) return r;  // not s->cnt: count_device uses that in work order
             if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
             SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
@@ -993,15 +1022,17 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
 }
 
 static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                       uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, void** alloc_out,
-                       uint64_t* total_out) {
+                       uint32_t flags, void* out_offs, void* positions, uint64_t capacity, void** alloc_out,
+                       uint64_t* total_out, const PackedSpec& spec = PackedSpec()) {
     if (!ix || !out_offs || !total_out) return SVFM_ERR_BAD_ARG;
     *total_out = 0;
     if (alloc_out) *alloc_out = nullptr;
     uint64_t bytes = 0;
     int rc = check_host_patterns(pats, offs, n, fixed_len, &bytes);
     if (rc) return rc;
-    out_offs[0] = 0;
+    const bool o32 = (flags & SVFM_OFFS32) != 0;   // out_offs is u32[n+1]
+    const size_t OW = o32 ? sizeof(uint32_t) : sizeof(uint64_t);
+    if (o32) static_cast<uint32_t*>(out_offs)[0] = 0; else static_cast<uint64_t*>(out_offs)[0] = 0;
     if (n == 0) return SVFM_OK;
     const uint64_t P = ix->type.pos_bits / 8;
     const ChunkPlan cp = plan_chunks(n);
@@ -1011,12 +1042,13 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         svfm_session* s = lease.s;
         PatternBatch pb;
         if ((rc = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return rc;
+        if ((rc = unpack_chunk(s, spec, pb))) return rc;
         if ((rc = s->out_offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
         void* d_positions = nullptr;
         uint64_t total = 0;
-        if ((rc = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return rc;
+        if ((rc = locate_device(s, pb, flags, s->out_offs.ptr, &d_positions, &total))) return rc;
         *total_out = total;
-        SVFM_CUDA(cudaMemcpyAsync(out_offs, s->out_offs.ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync(out_offs, s->out_offs.ptr, (n + 1) * OW, cudaMemcpyDeviceToHost, s->stream));
         void* dst = positions;
         if (alloc_out && total) {
             if (!(dst = result_alloc(total * P))) { cudaStreamSynchronize(s->stream); return SVFM_ERR_NOMEM; }
@@ -1059,10 +1091,11 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         if ((r = await_chunk(s, cp, g, c, pb))) return r;
         if (g_trace) { cudaStreamSynchronize(s->stream); }
         const double t_1 = g_trace ? now_ms() : 0;
+        if ((r = unpack_chunk(s, spec, pb))) return r;
         if ((r = s->out_offs.reserve((m + 1) * sizeof(uint64_t)))) return r;
         void* d_positions = nullptr;
         uint64_t total = 0;
-        if ((r = locate_device(s, pb, flags, (uint64_t*)s->out_offs.ptr, &d_positions, &total))) return r;
+        if ((r = locate_device(s, pb, flags, s->out_offs.ptr, &d_positions, &total))) return r;
         if (g_trace) { cudaStreamSynchronize(s->stream); }
         const double t_2 = g_trace ? now_ms() : 0;
         publish(c, total);
@@ -1074,12 +1107,14 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         }
         const bool last = (c + 1 == cp.chunks);
         const uint64_t n_offs = m + (last ? 1 : 0);
+        if (o32 && base + total > 0xffffffffull) { g_last_error = "SVFM_OFFS32: 2^32 occurrences or more"; return SVFM_ERR_TOO_LARGE; }
         if (base) {
-            add_base_kernel<<<grid_for(n_offs, 256, ix->device), 256, 0, s->stream>>>((uint64_t*)s->out_offs.ptr, n_offs, base);
+            if (o32) add_base_kernel<uint32_t><<<grid_for(n_offs, 256, ix->device), 256, 0, s->stream>>>((uint32_t*)s->out_offs.ptr, n_offs, (uint32_t)base);
+            else add_base_kernel<uint64_t><<<grid_for(n_offs, 256, ix->device), 256, 0, s->stream>>>((uint64_t*)s->out_offs.ptr, n_offs, base);
             g_launches++;
             SVFM_CUDA(cudaGetLastError());
         }
-        SVFM_CUDA(cudaMemcpyAsync(out_offs + a, s->out_offs.ptr, n_offs * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+        SVFM_CUDA(cudaMemcpyAsync((uint8_t*)out_offs + a * OW, s->out_offs.ptr, n_offs * OW, cudaMemcpyDeviceToHost, s->stream));
         if (total) {
             if (alloc_out) {
                 void* buf = result_alloc(total * P);
@@ -1236,15 +1271,76 @@ int svfm_count_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, 
 }
 
 int svfm_locate_batch(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                      uint32_t flags, uint64_t* out_offs, void* positions, uint64_t capacity, uint64_t* total) {
+                      uint32_t flags, void* out_offs, void* positions, uint64_t capacity, uint64_t* total) {
     if (capacity && !positions) return SVFM_ERR_BAD_ARG;
     return locate_host(ix, pats, offs, n, fixed_len, flags, out_offs, positions, capacity, nullptr, total);
 }
 
 int svfm_locate_batch_alloc(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
-                            uint32_t flags, uint64_t* out_offs, void** positions, uint64_t* total) {
+                            uint32_t flags, void* out_offs, void** positions, uint64_t* total) {
     if (!positions) return SVFM_ERR_BAD_ARG;
     return locate_host(ix, pats, offs, n, fixed_len, flags, out_offs, nullptr, 0, positions, total);
+}
+
+static int packed_spec(uint32_t len, uint32_t bits, uint32_t flags, PackedSpec* spec, uint32_t* bpp) {
+    if (len == 0) return SVFM_ERR_EMPTY_PATTERN;
+    if (bits < 1 || bits > 8 || (flags & SVFM_REVERSED)) return SVFM_ERR_BAD_ARG;
+    const uint64_t b = ((uint64_t)len * bits + 7) / 8;
+    if (b > 0xffffffffull) return SVFM_ERR_BAD_ARG;
+    spec->bits = bits;
+    spec->len = len;
+    *bpp = (uint32_t)b;
+    return SVFM_OK;
+}
+
+int svfm_count_batch_packed(svfm_index* ix, const uint8_t* packed, uint64_t n, uint32_t len, uint32_t bits, uint32_t flags,
+                            void* counts_out) {
+    if (!ix || (n && (!counts_out || !packed))) return SVFM_ERR_BAD_ARG;
+    PackedSpec spec;
+    uint32_t bpp = 0;
+    int rc = packed_spec(len, bits, flags, &spec, &bpp);
+    if (rc) return rc;
+    if (n == 0) return SVFM_OK;
+    return count_host(ix, packed, nullptr, n, bpp, flags, counts_out, spec);
+}
+
+int svfm_locate_batch_packed(svfm_index* ix, const uint8_t* packed, uint64_t n, uint32_t len, uint32_t bits, uint32_t flags,
+                             void* out_offs, void* positions, uint64_t capacity, uint64_t* total) {
+    if (capacity && !positions) return SVFM_ERR_BAD_ARG;
+    PackedSpec spec;
+    uint32_t bpp = 0;
+    int rc = packed_spec(len, bits, flags, &spec, &bpp);
+    if (rc) return rc;
+    return locate_host(ix, packed, nullptr, n, bpp, flags, out_offs, positions, capacity, nullptr, total, spec);
+}
+
+int svfm_pack_patterns(const uint8_t* pats, uint64_t n, uint32_t len, const uint8_t* table256, uint32_t bits, uint8_t* packed_out) {
+    if ((n && (!pats || !packed_out)) || bits < 1 || bits > 8 || len == 0) return SVFM_ERR_BAD_ARG;
+    const uint64_t bpp = ((uint64_t)len * bits + 7) / 8;
+    const uint32_t limit = 1u << bits;
+    unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw ? hw : 1, (n + 65535) / 65536 ? (n + 65535) / 65536 : 1);
+    std::atomic<int> bad{0};
+    auto work = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = a; i < b; i++) {
+            const uint8_t* p = pats + i * (uint64_t)len;
+            uint8_t* o = packed_out + i * bpp;
+            std::memset(o, 0, bpp);
+            for (uint32_t j = 0; j < len; j++) {
+                const uint32_t s = table256 ? table256[p[j]] : p[j];
+                if (s >= limit) { bad.store(1); continue; }
+                const uint32_t bit = j * bits;
+                o[bit >> 3] |= (uint8_t)(s << (bit & 7u));
+                if ((bit & 7u) + bits > 8u) o[(bit >> 3) + 1] |= (uint8_t)(s >> (8u - (bit & 7u)));
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    const uint64_t per = (n + nt - 1) / nt;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto& t : th) t.join();
+    return bad.load() ? SVFM_ERR_BAD_SYMBOL : SVFM_OK;
 }
 
 void svfm_free_positions(void* positions) {
@@ -1268,7 +1364,7 @@ int svfm_locate(svfm_index* ix, const uint8_t* pattern, uint64_t len, uint32_t f
     if (len == 0) return SVFM_ERR_EMPTY_PATTERN;
     if (len > 0xffffffffull) return SVFM_ERR_BAD_ARG;
     uint64_t offs2[2];
-    return svfm_locate_batch(ix, pattern, nullptr, 1, (uint32_t)len, flags, offs2, positions, capacity, total);
+    return svfm_locate_batch(ix, pattern, nullptr, 1, (uint32_t)len, flags & ~(uint32_t)SVFM_OFFS32, offs2, positions, capacity, total);
 }
 
 int svfm_session_create(svfm_index* ix, svfm_session** out) {
@@ -1312,7 +1408,7 @@ int svfm_count_batch_device(svfm_session* s, const uint8_t* d_pats, const uint64
     if (!s || (n && (!d_pats || !d_counts_out))) return SVFM_ERR_BAD_ARG;
     if (!d_offs && fixed_len == 0 && n) return SVFM_ERR_EMPTY_PATTERN;
     SVFM_CUDA(cudaSetDevice(s->ix->device));
-    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
+    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u, 0u};
     int rc = count_device(s, pb, d_counts_out);
     if (rc) return rc;
     // the error word is read back asynchronously; svfm_session_sync + the next call report it
@@ -1332,7 +1428,7 @@ int svfm_locate_batch_device(svfm_session* s, const uint8_t* d_pats, const uint6
         SVFM_CUDA(cudaMemsetAsync(d_out_offs, 0, (flags & SVFM_OFFS32) ? sizeof(uint32_t) : sizeof(uint64_t), s->stream));
         return SVFM_OK;
     }
-    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u};
+    PatternBatch pb{d_pats, d_offs, n, fixed_len, (flags & SVFM_REVERSED) ? 1u : 0u, 0u};
     return locate_device(s, pb, flags, d_out_offs, d_positions, total);
 }
 

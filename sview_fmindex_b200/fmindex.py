@@ -275,10 +275,57 @@ class FmIndex:
             pos = np.zeros(0, dtype=self.type.pos_dtype)
         return out_offs, pos
 
-    def locate_batch(self, patterns, sorted_: bool = False, reversed_: bool = False):
-        """-> (out_offs u64[n+1], positions P[total]); pattern i owns positions[out_offs[i]:out_offs[i+1]]."""
+    def locate_batch(self, patterns, sorted_: bool = False, reversed_: bool = False, offs32: bool = False):
+        """-> (out_offs u64[n+1] (u32 with offs32), positions P[total]); pattern i owns positions[out_offs[i]:out_offs[i+1]]."""
         flags = (_ffi.SVFM_SORTED if sorted_ else 0) | (_ffi.SVFM_REVERSED if reversed_ else 0)
-        return self._locate_batch_raw(patterns, flags)
+        if not offs32:
+            return self._locate_batch_raw(patterns, flags)
+        data, offs, n, fixed = _pack_patterns(patterns)
+        out_offs = np.zeros(n + 1, dtype=np.uint32)
+        ptr, total = C.c_void_p(), C.c_uint64()
+        _raise(_ffi.lib().svfm_locate_batch_alloc(self._h, data.ctypes.data, offs.ctypes.data if offs is not None else None, n, fixed,
+                                                  flags | _ffi.SVFM_OFFS32, out_offs.ctypes.data, C.byref(ptr), C.byref(total)))
+        return out_offs, self._take_positions(ptr, int(total.value))
+
+    def _take_positions(self, ptr, t: int) -> np.ndarray:
+        if not t:
+            return np.zeros(0, dtype=self.type.pos_dtype)
+        pos = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32 if self.type.pos_bits == 32 else C.c_uint64)), shape=(t,)).copy()
+        _ffi.lib().svfm_free_positions(ptr)
+        return pos
+
+    # ---- packed fixed-length batches (include/svfm.h, "packed fixed-length batches") ----------------------------
+    @staticmethod
+    def pack_patterns(patterns: np.ndarray, table, bits: int) -> np.ndarray:
+        """2-D uint8 patterns -> packed (n, ceil(len*bits/8)) uint8; table = 256-entry encoding table or None."""
+        p = np.ascontiguousarray(patterns, dtype=np.uint8)
+        n, ln = p.shape
+        out = np.zeros((n, (ln * bits + 7) // 8), dtype=np.uint8)
+        tbl = np.ascontiguousarray(table, dtype=np.uint8) if table is not None else None
+        _raise(_ffi.lib().svfm_pack_patterns(p.ctypes.data, n, ln, tbl.ctypes.data if tbl is not None else None, bits, out.ctypes.data))
+        return out
+
+    def count_batch_packed(self, packed: np.ndarray, length: int, bits: int) -> np.ndarray:
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        n = pk.shape[0]
+        out = np.zeros(n, dtype=self.type.pos_dtype)
+        _raise(_ffi.lib().svfm_count_batch_packed(self._h, pk.ctypes.data, n, length, bits, 0, out.ctypes.data))
+        return out
+
+    def locate_batch_packed(self, packed: np.ndarray, length: int, bits: int, offs32: bool = False, sorted_: bool = False):
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        n = pk.shape[0]
+        flags = (_ffi.SVFM_SORTED if sorted_ else 0) | (_ffi.SVFM_OFFS32 if offs32 else 0)
+        out_offs = np.zeros(n + 1, dtype=np.uint32 if offs32 else np.uint64)
+        total = C.c_uint64()
+        rc = _ffi.lib().svfm_locate_batch_packed(self._h, pk.ctypes.data, n, length, bits, flags, out_offs.ctypes.data, None, 0, C.byref(total))
+        if rc not in (_ffi.SVFM_OK, _ffi.SVFM_ERR_CAPACITY):
+            _raise(rc)
+        pos = np.zeros(int(total.value), dtype=self.type.pos_dtype)
+        if pos.size:
+            _raise(_ffi.lib().svfm_locate_batch_packed(self._h, pk.ctypes.data, n, length, bits, flags, out_offs.ctypes.data,
+                                                       pos.ctypes.data, pos.size, C.byref(total)))
+        return out_offs, pos
 
 
 # ---- builder (GPU suffix sort; SURVEY.md section 8f.1) ----------------------------------------------
@@ -330,7 +377,8 @@ class FmIndexBuilder:
             self.kmer_size = v
         elif kind == "MaxMemory":
             swsc, k = self.symbol_count + 1, 2
-            while swsc ** k * (self.type.pos_bits // 8) <= v:
+            # lookup_table_config.rs:41-53, plus: (S+1)^k must fit the u32 the reference stores it in (count_array.rs:70)
+            while swsc ** k * (self.type.pos_bits // 8) <= v and swsc ** k <= 0xFFFFFFFF:
                 k += 1
             self.kmer_size = k - 1
         else:

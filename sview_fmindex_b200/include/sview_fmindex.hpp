@@ -281,10 +281,10 @@ class FmIndexBuilder {
         if (c.by_memory) {
             uint64_t swsc = (uint64_t)symbol_count_ + 1;
             uint32_t k = 2;
-            for (;;) {
-                unsigned __int128 sz = sizeof(P);
-                for (uint32_t e = 0; e < k; e++) sz *= swsc;
-                if (sz <= c.max_memory) k++; else break;
+            for (;;) {  // lookup_table_config.rs:41-53, plus: (S+1)^k must fit the u32 the reference stores it in
+                unsigned __int128 entries = 1;
+                for (uint32_t e = 0; e < k; e++) entries *= swsc;
+                if (entries * sizeof(P) <= c.max_memory && entries <= (unsigned __int128)0xffffffffu) k++; else break;
             }
             kmer_ = k - 1;
         } else {

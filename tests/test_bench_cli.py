@@ -51,3 +51,24 @@ def test_build_locate_round_trip(oracle, tmp_path, t_wild):
     assert len(lines) == len(pats) == 3005
     for pat, line in zip(pats, lines):
         assert line == b",".join(str(int(x)).encode() for x in ora.locate(pat)), pat
+    # the mmap variant (bench/src/locate/sview_mmap.rs) loads the same blob out of the page cache: identical result file
+    first = open(os.path.join(d, stem + "-results.txt"), "rb").read()
+    os.remove(os.path.join(d, stem + "-results.txt"))
+    os.environ["MMAP_ADVICE_SEQUENTIAL"] = "1"
+    try:
+        assert bench_cli.main(["locate", "-a", "sview-mmap"] + args) == 0
+    finally:
+        del os.environ["MMAP_ADVICE_SEQUENTIAL"]
+    assert open(os.path.join(d, stem + "-results.txt"), "rb").read() == first
+
+
+def test_mmap_blob_is_a_read_only_mapping(tmp_path):
+    from sview_fmindex_b200 import bench_cli
+    p = tmp_path / "x.blob"
+    p.write_bytes(bytes(range(256)) * 64)
+    os.environ["MMAP_ADVICE_RANDOM"] = "1"
+    try:
+        m = bench_cli.map_blob(str(p))
+    finally:
+        del os.environ["MMAP_ADVICE_RANDOM"]
+    assert isinstance(m, np.memmap) and m.size == 256 * 64 and int(m[257]) == 1 and not m.flags.writeable

@@ -462,3 +462,41 @@ def test_concurrent_callers(oracle, fm):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+def test_packed_patterns_and_u32_offsets(oracle, fm):
+    """The byte-saving variants of the host entry points (include/svfm.h): 2- and 5-bit packed fixed-length patterns
+    and u32 CSR offsets give exactly the results of the plain calls, across chunk sizes."""
+    from sview_fmindex_b200 import _ffi
+    L = _ffi.lib()
+    rng = np.random.default_rng(606)
+    n = 300_000
+    try:
+        for symbols, alphabet, bits, ln, with_wildcard in (([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"], b"ACGT", 2, 20, False),
+                                                           ([b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"], b"ACGTN", 3, 7, False),
+                                                           ([bytes([c]) for c in b"ACDEFGHIKLMNPQRSTVWY"], b"ACDEFGHIKLMNPQRSTVWY", 5, 12, True)):
+            text = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=n)].copy()
+            planes = 3 if len(symbols) <= 7 else 5
+            ora, gpu, table, sc = _pair(oracle, fm, bytes(text), symbols, 32, planes, 64, 3, 2, with_wildcard=with_wildcard)
+            m = 60_000
+            starts = rng.integers(0, n - ln, size=m)
+            pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
+            pats[::6, ln // 2] = alphabet[0]
+            oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
+            packed = gpu.pack_patterns(pats, table, bits)
+            assert packed.shape == (m, (ln * bits + 7) // 8)
+            for chunk in (0, 9000):
+                assert L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, chunk) == 0
+                assert np.array_equal(gpu.count_batch_packed(packed, ln, bits).astype(np.uint64), oc)
+                offs, pos = gpu.locate_batch_packed(packed, ln, bits)
+                assert np.array_equal(offs, oo) and np.array_equal(pos.astype(np.uint64), op_.astype(np.uint64))
+                offs32, pos32 = gpu.locate_batch_packed(packed, ln, bits, offs32=True)
+                assert offs32.dtype == np.uint32 and np.array_equal(offs32.astype(np.uint64), oo) and np.array_equal(pos32, pos)
+                o3, p3 = gpu.locate_batch(pats, offs32=True)
+                assert o3.dtype == np.uint32 and np.array_equal(o3.astype(np.uint64), oo) and np.array_equal(p3, pos)
+            # a symbol index that does not fit `bits` is refused by the packer; one >= symbol_count by the search
+            with pytest.raises(fm.SvfmError):
+                gpu.pack_patterns(np.full((4, ln), 255, dtype=np.uint8), None, bits)
+            gpu.close()
+    finally:
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)

@@ -23,15 +23,18 @@ def fm():
 
 def test_library_exports_every_declared_symbol(fm):
     from sview_fmindex_b200 import _ffi
-    lib = C.CDLL(_ffi.LIB_PATH)
-    for header, table in (("svfm.h", _ffi.EXPORTS), ("svfm_bench.h", _ffi.BENCH_EXPORTS)):
+    for header, table, path in (("svfm.h", _ffi.EXPORTS, _ffi.LIB_PATH), ("svfm_bench.h", _ffi.BENCH_EXPORTS, _ffi.BENCH_LIB_PATH)):
+        lib = C.CDLL(path)
         hdr = open(os.path.join(ROOT, "include", header)).read()
         declared = set(re.findall(r"\b(svfm_[a-z0-9_]+)\s*\(", hdr))
         assert declared
         for name in sorted(declared):
-            assert hasattr(lib, name), f"libsvfm.so does not export {name}"
+            assert hasattr(lib, name), f"{os.path.basename(path)} does not export {name}"
         bound = {e[0] for e in table}
         assert declared == bound, (header, declared - bound, bound - declared)
+    # the measurement helpers are not part of the product library
+    product = C.CDLL(_ffi.LIB_PATH)
+    assert not any(hasattr(product, e[0]) for e in _ffi.BENCH_EXPORTS)
     assert b"sm_100a" in _ffi.lib().svfm_version()
 
 
@@ -160,3 +163,47 @@ def test_bench_reference_arm_contract():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_roofline_traffic_file_names_existing_kernels():
+    """profiles/roofline_traffic.json (ncu DRAM bytes per kernel, read by bench.py) is regenerated by tools/roofline_traffic.py
+    after kernel changes; a kernel name in it that no longer exists in the sources means the file has gone stale."""
+    import json
+    import sys
+    doc = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    assert doc["configs"], "no configuration in profiles/roofline_traffic.json"
+    src = ""
+    csrc = os.path.join(ROOT, "sview_fmindex_b200", "csrc")
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh")):
+            src += open(os.path.join(csrc, f), errors="replace").read()
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, cfg in doc["configs"].items():
+        assert name in bench.CONFIGS, name
+        assert cfg["patterns_per_step"] == bench.CONFIGS[name]["batch"], (name, "batch size changed: re-profile")
+        phases = {k["phase"] for k in cfg["kernels"]}
+        assert phases <= set(bench.PHASES) | {"other"}, phases
+        for k in cfg["kernels"]:
+            if k["kernel"].startswith("svfm::"):
+                fn = k["kernel"].split("::")[-1]
+                assert re.search(rf"\b{fn}\b", src), f"{name}: kernel {fn} is not in csrc any more -- regenerate the traffic file"
+
+
+def test_kmer_table_length_overflow_is_an_invalid_config():
+    """(S+1)^k is a u32 in the reference (count_array.rs:70, u32::pow): KmerSize(14) on a 4-symbol alphabet needs 5^14 =
+    6.1e9 entries.  The reference panics or wraps; here the builder refuses the configuration, and MaxMemory never picks it."""
+    import sview_fmindex_b200 as fm
+    enc = fm.EncodingTable.from_symbols([b"A", b"C", b"G", b"T"])
+    it = fm.IndexType(32, 2, 64, True)
+    b = fm.FmIndexBuilder(1000, 4, enc, it)
+    with pytest.raises(fm.BuildError) as e:
+        b.set_lookup_table_config(fm.LookupTableConfig.KmerSize(14))
+    assert e.value.code == 14
+    b = fm.FmIndexBuilder(1000, 4, enc, it)
+    b.set_lookup_table_config(fm.LookupTableConfig.KmerSize(13))      # 5^13 = 1.2e9 fits
+    assert b.kmer_size == 13
+    b.set_lookup_table_config(fm.LookupTableConfig.MaxMemory(32 << 30))  # 5^14 * 4 B = 24.4 GB would fit the budget
+    assert b.kmer_size == 13
+    b.set_lookup_table_config(fm.LookupTableConfig.MaxMemory(1 << 20))   # reference arithmetic below the bound
+    assert b.kmer_size == 7                                              # 5^7 * 4 B = 312 500 <= 1 MiB < 5^8 * 4 B

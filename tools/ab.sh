@@ -12,7 +12,8 @@ import json,sys
 d=json.load(open("gpurun_out/ab_%s.json"%sys.argv[1]))
 ph=d["phase_ms_per_step"]
 e=d.get("e2e") or {}
-print("%-12s %.3f ms/step  %.2f G/s  count-only %.2f G/s  e2e %.2f | "%(sys.argv[1], d["ms_per_step"], d["value"]/1e9, d["count_only_patterns_per_s"]/1e9, e.get("value",0)/1e9) + "  ".join("%s=%.2f"%(k.split("(")[0],v) for k,v in ph.items()))
+ea=d.get("e2e_ascii") or {}
+print("%-12s %.3f ms/step  %.2f G/s  count-only %.2f G/s  e2e %.2f (ascii %.2f) | "%(sys.argv[1], d["ms_per_step"], d["value"]/1e9, (d.get("count_only_patterns_per_s") or 0)/1e9, e.get("value",0)/1e9, ea.get("value",0)/1e9) + "  ".join("%s=%.2f"%(k.split("(")[0],v) for k,v in ph.items()))
 PY
 }
 if [ $# -eq 0 ]; then run default ""; fi

@@ -12,7 +12,7 @@ mkdir -p $OUT/$NAME
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 OBJS=""
-for f in svfm_api.cu builder.cu benchtools.cu inst_p32_v32.cu inst_p32_v64.cu inst_p32_v128.cu inst_p64_v32.cu inst_p64_v64.cu inst_p64_v128.cu; do
+for f in svfm_api.cu builder.cu inst_p32_v32.cu inst_p32_v64.cu inst_p32_v128.cu inst_p64_v32.cu inst_p64_v64.cu inst_p64_v128.cu; do
   o=$SRC/${f%.cu}.o
   for v in $FILES; do
     if [ "$v" == "$f" ]; then
