@@ -450,6 +450,7 @@ def run_ours(args):
         for s in range(n_host):
             chk(L, L.svfm_bench_synth_patterns(d_text.data_ptr(), n, d_pe.data_ptr(), d_se.data_ptr(), Be, plen,
                                                args.seed + 77_000 * (rank + 1) + s, None), "synth_patterns(e2e)")
+            torch.cuda.synchronize()
             p = L.svfm_host_alloc(Be * plen)
             q = L.svfm_host_alloc(Be * bpp)
             if not p or not q:
@@ -499,6 +500,7 @@ def run_ours(args):
             i_last = (Ke - 1) % n_host
             chk(L, L.svfm_bench_synth_patterns(d_text.data_ptr(), n, d_pe.data_ptr(), d_se.data_ptr(), Be, plen,
                                                args.seed + 77_000 * (rank + 1) + i_last, None))
+            torch.cuda.synchronize()   # the generator runs on the default stream, the session's stream does not wait for it
             if mode == "count":
                 d_c = torch.empty(Be, dtype=t_pos, device="cuda")
                 chk(L, L.svfm_count_batch_device(sess, d_pe.data_ptr(), None, Be, plen, 0, d_c.data_ptr()))

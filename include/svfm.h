@@ -98,8 +98,9 @@ int svfm_load_device(const uint8_t* d_blob, size_t blob_len, svfm_type t, int de
 void svfm_free(svfm_index* ix);
 int svfm_index_info(const svfm_index* ix, svfm_info* out);
 /* Device memory held by the handle, in bytes: out[0] the blob copy, out[1] the extended k-mer table, out[2] the
- * interleaved occ copy, out[3] scratch arenas of the idle sessions / upload staging (grow-only until svfm_free). */
-int svfm_index_memory(svfm_index* ix, uint64_t out[4]);
+ * interleaved occ copy, out[3] scratch arenas of the idle sessions / upload staging (grow-only until svfm_free),
+ * out[4] the packed text copy. */
+int svfm_index_memory(svfm_index* ix, uint64_t out[5]);
 /* Host-only part of load: validate + report sizes without touching a device (LoadError paths). */
 int svfm_check_blob(const uint8_t* blob, size_t blob_len, svfm_type t, svfm_info* out, uint64_t err_detail[2]);
 
@@ -188,7 +189,8 @@ void svfm_host_free(void* p);
  *                      UINT64_MAX = never; default SVFM_TUNE_AUTO = never when the index has an extended k-mer table
  *                      -- nothing is left to share after the lookup -- else 131072; env SVFM_SORT_MIN).
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
- *                      pipeline upload / kernels / download (0 = one chunk; default 8 Mi; env SVFM_CHUNK).
+ *                      pipeline upload / kernels / download (0 = one chunk; default SVFM_TUNE_AUTO = 8 Mi, 16 Mi for
+ *                      packed patterns of at most 8 bytes; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
  *                      kept sorted by SA position and moves through the index as streams (default SVFM_TUNE_AUTO = the
  *                      measured break-even with the plain search kernel on a 1 Gbp index: 5 Mi patterns with a 2^24-entry
@@ -204,9 +206,22 @@ void svfm_host_free(void* p);
  * SVFM_TUNE_BUCKET_SORTBACK : how a reordered batch gets back into the caller's order.  1 (default): locate writes its
  *                      records straight into buckets of 8192 pattern indices and one kernel finishes every bucket in shared
  *                      memory; `count` groups by the top index bits and scatters.  0: radix sorts by pattern index
- *                      (env SVFM_BUCKET_SORTBACK). */
+ *                      (env SVFM_BUCKET_SORTBACK).
+ * SVFM_TUNE_SMALL_MAX : host batches of at most this many patterns (and at most 256 KiB of pattern bytes) run as ONE kernel
+ *                      launch that searches and locates, with patterns and results in mapped pinned host memory -- one
+ *                      launch and one synchronisation per call instead of six runtime calls; a pattern with more than 8
+ *                      occurrences sends its batch through the general pipeline (default and maximum 4096; 0 = never;
+ *                      env SVFM_SMALL_MAX).
+ * SVFM_TUNE_TEXT     : indexes loaded from now on also get a packed copy of the indexed text (1, 2, 4 or 8 bits per symbol),
+ *                      recovered from the blob itself at load.  The search kernel then finishes a pattern whose SA interval
+ *                      is down to a few rows with many symbols left (150 bp reads after ~16 symbols) by locating the
+ *                      candidates and comparing the rest of the pattern with the text -- a few sectors instead of one
+ *                      random line per remaining symbol (1 = build, the default; 0 = index only; env SVFM_TEXT).
+ * SVFM_TUNE_L2_PERSIST: indexes loaded from now on whose extended k-mer table takes at most this many bytes (default 64 MiB;
+ *                      0 = never) mark it persisting in L2 for all their kernels (cudaAccessPolicyWindow).  The default
+ *                      2 GiB table is never pinned; this serves deployments that cap SVFM_TUNE_EXT_BITS (env SVFM_L2_PERSIST). */
 enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
-       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6 };
+       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9 };
 #define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */

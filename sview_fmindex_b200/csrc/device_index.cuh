@@ -38,6 +38,10 @@ struct DevIndex {
     const uint8_t* ilv;
     uint32_t ilv_stride;              // bytes per entry (32, 64, 128 or a multiple of 128)
     uint32_t ilv_ck_off;              // byte offset of the checkpoint row inside an entry
+    // packed copy of the indexed text, derived from the blob at load (search_kernels.cuh, "text verification"): symbol i =
+    // rank among the occurring symbols, text_bits (1, 2, 4 or 8) bits each, little-endian inside 32-bit words; NULL = not built
+    const uint32_t* text;
+    uint32_t text_bits;
 };
 
 // the symbol maps alone (kernels that do not touch the index arrays)

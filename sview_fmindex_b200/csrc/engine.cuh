@@ -40,6 +40,10 @@ struct svfm_index {
     void* d_ext = nullptr;         // P[2 * ext_entries]
     uint8_t* d_ilv = nullptr;      // interleaved occ copy (blocks_len entries of ilv_stride bytes), or NULL
     uint32_t ilv_stride = 0, ilv_ck_off = 0;
+    uint64_t l2_window_bytes = 0;  // > 0: the extended table is small enough to sit under an L2 persisting access window
+    uint32_t* d_text = nullptr;    // packed text copy (text verification), or NULL
+    uint32_t text_bits = 0;
+    uint64_t text_bytes = 0;
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
     std::vector<svfm_uploader*> up_pool;  // idle uploaders
@@ -61,11 +65,15 @@ struct svfm_session {
     svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions
     svfm::DeviceBuffer rec_key, rec_key_alt, first;          // radix sort-back of (pattern index -> position) records (SVFM_SORTED)
     svfm::DeviceBuffer sb_hist, sb_base, sb_cursor, sb_recs; // bucketed sort-back
+    svfm::DeviceBuffer resolved;                             // text verification: per work item, sp holds the position
     svfm::DeviceBuffer heavy_sp, heavy_cnt, heavy_obase, heavy_pat, heavy_offs;
     unsigned long long* d_counters = nullptr;                // [0] heavy patterns seen by search, [1] heavy list length,
                                                              // [2] SA rows of the batch (bucketed sort-back)
     int* d_err = nullptr;
     uint64_t* h_pinned = nullptr;  // [0] = total, [1] = err bits
+    uint64_t reserve_n = 0;        // host-buffer calls: size the scratch for at least this many patterns (the call's largest chunk),
+                                   // so that every worker session grows its buffers once instead of whenever it meets a larger chunk
+    uint8_t* h_small = nullptr;    // small-batch path: mapped pinned arena (patterns | offsets | counts | slots | status)
     // per-phase timing (svfm_session_set_timing)
     bool timing = false;
     struct Span { int phase; cudaEvent_t e0, e1; };
@@ -76,6 +84,8 @@ struct svfm_session {
 };
 
 namespace svfm {
+
+static inline uint64_t rsv(const svfm_session* s, uint64_t n) { return n > s->reserve_n ? n : s->reserve_n; }
 
 constexpr int MAX_DYNAMIC_SMEM = 200 * 1024;  // opt-in dynamic shared memory per CTA (B200: up to 227 KB)
 
@@ -111,6 +121,8 @@ static DevIndex<P> make_dev_index(const svfm_index* ix) {
     d.ilv = ix->d_ilv;
     d.ilv_stride = ix->ilv_stride;
     d.ilv_ck_off = ix->ilv_ck_off;
+    d.text = ix->d_text;
+    d.text_bits = ix->text_bits;
     return d;
 }
 
@@ -193,14 +205,22 @@ static int bits_for(uint64_t n) {  // smallest b with 2^b >= n
 }
 
 
+constexpr uint32_t SEARCH_STAGE_MAX = 44 * 1024;
+
 // One launch of the search kernel: keys/idx (or NULL) in, sp/cnt out.
 template <class P, int NPL, int VBITS>
 static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                      void* d_sp_work, void* d_cnt_work, const SbOut& sb) {
-    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+                      void* d_sp_work, void* d_cnt_work, const SbOut& sb, uint8_t* d_resolved) {
+    DevIndex<P> dix = make_dev_index<P>(s->ix);
+    if (!d_resolved && d_sp_work) dix.text = nullptr;   // locate without a flag array: rows only (count may always verify)
     const bool ilv = dix.ilv != nullptr;
-    const int grid = ilv ? resident_grid(search_kernel<P, NPL, VBITS, true>, pb.n, SEARCH_THREADS, s->ix->device)
-                         : resident_grid(search_kernel<P, NPL, VBITS, false>, pb.n, SEARCH_THREADS, s->ix->device);
+    // dynamic shared memory for the staged pattern bytes of one CTA (search_kernels.cuh): up to ~44 KB, i.e. patterns of up
+    // to 176 bytes in a fixed-length batch; less when the patterns are short (occupancy)
+    uint32_t stage = 0;
+    if (!idx) {
+        const uint64_t want = pb.offs ? (uint64_t)SEARCH_STAGE_MAX : (uint64_t)SEARCH_THREADS * pb.fixed_len + 4;
+        stage = (uint32_t)(want < (uint64_t)SEARCH_STAGE_MAX ? ((want + 15) & ~(uint64_t)15) : (uint64_t)SEARCH_STAGE_MAX);
+    }
     SearchIO<P> io{};
     io.keys = keys;
     io.idx = idx;
@@ -210,10 +230,63 @@ static int run_search(svfm_session* s, const PatternBatch& pb, const uint64_t* k
     io.heavy_seen = s->d_counters;
     io.err = s->d_err;
     io.sb = sb;
+    io.resolved_out = d_resolved;
+    auto launch = [&](auto kernel) -> int {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->ix->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SEARCH_THREADS, stage) != cudaSuccess || per_sm < 1) per_sm = 1;
+        uint64_t blocks = (pb.n + SEARCH_THREADS - 1) / SEARCH_THREADS;
+        const uint64_t cap = (uint64_t)sms * per_sm * 4;   // 4 resident waves (measured in round 1: 13 % faster than one)
+        if (blocks > cap) blocks = cap;
+        if (blocks == 0) blocks = 1;
+        kernel<<<(unsigned)blocks, SEARCH_THREADS, stage, s->stream>>>(dix, pb, io, stage);
+        SVFM_CUDA(cudaGetLastError());
+        return SVFM_OK;
+    };
     PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
-    if (ilv) search_kernel<P, NPL, VBITS, true><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
-    else search_kernel<P, NPL, VBITS, false><<<grid, SEARCH_THREADS, 0, s->stream>>>(dix, pb, io);
+    return ilv ? launch(search_kernel<P, NPL, VBITS, true>) : launch(search_kernel<P, NPL, VBITS, false>);
+}
+
+// Small batches: one launch, inputs and outputs in mapped pinned host memory (search_kernels.cuh, small_batch_kernel).
+constexpr uint64_t SMALL_MAX_PATTERNS = 4096;
+constexpr uint64_t SMALL_MAX_BYTES = 256 << 10;
+constexpr uint32_t SMALL_SLOTS = 8;
+template <class P, int NPL, int VBITS>
+static int run_small(svfm_session* s, const PatternBatch& pb, const SmallOut& out) {
+    const DevIndex<P> dix = make_dev_index<P>(s->ix);
+    const unsigned grid = (unsigned)((pb.n + 127) / 128);
+    PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+    if (dix.ilv) small_batch_kernel<P, NPL, VBITS, true><<<grid, 128, 0, s->stream>>>(dix, pb, out);
+    else small_batch_kernel<P, NPL, VBITS, false><<<grid, 128, 0, s->stream>>>(dix, pb, out);
     SVFM_CUDA(cudaGetLastError());
+    return SVFM_OK;
+}
+
+// Packed text copy for the text verification (search_kernels.cuh), built once per index after the interleaved occ copy.
+template <class P, int NPL, int VBITS>
+static int run_build_text(svfm_index* ix) {
+    const uint64_t s_eff = ix->symbols_present;
+    const uint64_t n = ix->text_len;
+    if (s_eff < 1 || n == 0) return SVFM_OK;
+    const uint32_t bits = s_eff <= 2 ? 1 : s_eff <= 4 ? 2 : s_eff <= 16 ? 4 : 8;
+    const uint64_t bytes = ((n * bits + 31) / 32) * 4 + 16;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 8) { (void)cudaGetLastError(); return SVFM_OK; }
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { (void)cudaGetLastError(); return SVFM_OK; }   // optional structure
+    cudaError_t e = cudaMemset(d, 0, bytes);
+    if (e == cudaSuccess) {
+        const DevIndex<P> dix = make_dev_index<P>(ix);
+        const int grid = grid_for(n, 256, ix->device) * 4;
+        if (dix.ilv) text_build_kernel<P, NPL, VBITS, true><<<grid, 256>>>(dix, n, bits, d);
+        else text_build_kernel<P, NPL, VBITS, false><<<grid, 256>>>(dix, n, bits, d);
+        g_launches++;
+        e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) { cudaFree(d); SVFM_CUDA(e); }
+    ix->d_text = d;
+    ix->text_bits = bits;
+    ix->text_bytes = bytes;
     return SVFM_OK;
 }
 
@@ -300,9 +373,10 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     using Item = SweepItem<P, R>;
     const uint64_t n_tiles = (n + ROUND_TILE - 1) / ROUND_TILE;
     int rc;
-    if ((rc = s->vals0.reserve(n * 4)) || (rc = s->sweep_desc.reserve(n_tiles * nb_max * 4))) return rc;
+    const uint64_t rn = rsv(s, n);
+    if ((rc = s->vals0.reserve(rn * 4)) || (rc = s->sweep_desc.reserve((rn + ROUND_TILE - 1) / ROUND_TILE * nb_max * 4))) return rc;
     const bool partitions = rounds > 1;
-    if (partitions && ((rc = s->items0.reserve(n * sizeof(Item))) || (rc = s->items1.reserve(n * sizeof(Item))))) return rc;
+    if (partitions && ((rc = s->items0.reserve(rn * sizeof(Item))) || (rc = s->items1.reserve(rn * sizeof(Item))))) return rc;
     Item* items[2] = {(Item*)s->items0.ptr, (Item*)s->items1.ptr};
     SweepPre pre{};
     if ((rc = run_sweep_presort<R>(s, pb, plan, rounds, &pre))) return rc;  // pack + radix sort by table index (svfm_api.cu)
@@ -418,7 +492,7 @@ static int run_scan(svfm_session* s, uint64_t n, const void* d_cnt, uint64_t* d_
 template <class P, int NPL, int VBITS>
 static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
                       const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
-                      void* d_recs, unsigned long long* d_cursor) {
+                      void* d_recs, unsigned long long* d_cursor, const uint8_t* d_resolved) {
     if (total == 0) return SVFM_OK;
     const DevIndex<P> dix = make_dev_index<P>(s->ix);
     HeavyList<P> heavy{nullptr, nullptr, nullptr, nullptr, s->d_counters + 1, 0};
@@ -441,7 +515,7 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
         auto launch = [&](auto kernel) {
             const int grid = resident_grid(kernel, n, LOCATE_THREADS, s->ix->device);
             kernel<<<grid, LOCATE_THREADS, 0, s->stream>>>(dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n,
-                                                           (P*)d_positions, d_rec_key, heavy, bk);
+                                                           (P*)d_positions, d_rec_key, heavy, bk, d_resolved);
         };
         if (dix.ilv) {
             if (bucket) launch(locate_warp_kernel<P, NPL, VBITS, true, true>);
@@ -484,13 +558,15 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
 // ---- per-(Position, Vector) entry points; `planes` picks Block2..Block6 ------------------------------------------
 struct TypeOps {
     int (*search)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                  void* d_sp_work, void* d_cnt_work, const SbOut& sb);
+                  void* d_sp_work, void* d_cnt_work, const SbOut& sb, uint8_t* d_resolved);
     int (*build_ext)(uint32_t planes, svfm_index* ix, uint64_t ext_bits);
+    int (*build_text)(uint32_t planes, svfm_index* ix);
     int (*search_sweep)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,
                         void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb);
+    int (*small)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SmallOut& out);
     int (*locate)(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
                   const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
-                  void* d_recs, unsigned long long* d_cursor);
+                  void* d_recs, unsigned long long* d_cursor, const uint8_t* d_resolved);
 };
 
 #define SVFM_PLANES_SWITCH(P, VB, FN, ...)          \
@@ -506,24 +582,31 @@ struct TypeOps {
 // One translation unit per (P, VB): defines `const TypeOps NAME`.
 #define SVFM_DEFINE_TYPE_OPS(NAME, P, VB)                                                                                          \
     static int NAME##_search(uint32_t planes, svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx,   \
-                             uint32_t bits, void* d_sp_work, void* d_cnt_work, const SbOut& sb) {                       \
-        SVFM_PLANES_SWITCH(P, VB, run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb)                               \
+                             uint32_t bits, void* d_sp_work, void* d_cnt_work, const SbOut& sb, uint8_t* d_resolved) {  \
+        SVFM_PLANES_SWITCH(P, VB, run_search, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb, d_resolved)                   \
     }                                                                                                                               \
     static int NAME##_build_ext(uint32_t planes, svfm_index* ix, uint64_t ext_bits) {                                               \
         SVFM_PLANES_SWITCH(P, VB, run_build_ext, ix, ext_bits)                                                                      \
+    }                                                                                                                               \
+    static int NAME##_build_text(uint32_t planes, svfm_index* ix) {                                                                 \
+        SVFM_PLANES_SWITCH(P, VB, run_build_text, ix)                                                                               \
     }                                                                                                                               \
     static int NAME##_search_sweep(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,  \
                                    void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {      \
         SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb)               \
     }                                                                                                                               \
+    static int NAME##_small(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SmallOut& out) {                        \
+        SVFM_PLANES_SWITCH(P, VB, run_small, s, pb, out)                                                                            \
+    }                                                                                                                               \
     static int NAME##_locate(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work,              \
                              const void* d_cnt_work, const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen,                   \
-                             void* d_positions, uint32_t* d_rec_key, void* d_recs, unsigned long long* d_cursor) {                  \
+                             void* d_positions, uint32_t* d_rec_key, void* d_recs, unsigned long long* d_cursor,                    \
+                             const uint8_t* d_resolved) {                                                                           \
         SVFM_PLANES_SWITCH(P, VB, run_locate, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key,  \
-                           d_recs, d_cursor)                                                                                        \
+                           d_recs, d_cursor, d_resolved)                                                                            \
     }                                                                                                                               \
     extern const TypeOps NAME;                                                                                                      \
-    const TypeOps NAME = {NAME##_search, NAME##_build_ext, NAME##_search_sweep, NAME##_locate};
+    const TypeOps NAME = {NAME##_search, NAME##_build_ext, NAME##_build_text, NAME##_search_sweep, NAME##_small, NAME##_locate};
 
 extern const TypeOps ops_p32_v32, ops_p32_v64, ops_p32_v128, ops_p64_v32, ops_p64_v64, ops_p64_v128;
 

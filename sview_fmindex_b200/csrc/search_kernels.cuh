@@ -144,90 +144,276 @@ struct SearchIO {
     unsigned long long* heavy_seen;  // nullable
     int* err;
     SbOut sb;
+    uint8_t* resolved_out;  // work order, nullable: 1 = sp_out holds the TEXT POSITION of the single occurrence (text verification)
 };
 
-// FmIndex::get_pos_range (locate/with_slice.rs:21-33) for one pattern per thread, grid-stride.
-// Work item w handles pattern idx[w] (idx == NULL: identity).  With keys != NULL the last 64/bits symbols of
-// the pattern come out of keys[w] (see pack_keys_kernel).  Outputs in WORK order, coalesced.
+// FmIndex::write_locations_to_buffer (locate/mod.rs:14-37) for ONE SA row: LF-walk to the nearest
+// sampled row (BwmView::get_pre_rank_and_symidx, bwm/mod.rs:217-236), then
+// SuffixArrayView::get_location_of (suffix_array/mod.rs:100-105).
+template <class P, int NPL, int VBITS, bool ILV>
+__device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restrict__ s_count, P pos) {
+    P offset = 0;
+    for (;;) {
+        // pos % sampling_ratio != 0
+        uint64_t quot;
+        bool sampled;
+        if (ix.ratio_mask != 0xffffffffu) {
+            sampled = ((uint32_t)pos & ix.ratio_mask) == 0;
+            quot = (uint64_t)pos >> ix.ratio_shift;
+        } else {
+            quot = (uint64_t)pos / ix.sampling_ratio;
+            sampled = (quot * ix.sampling_ratio == (uint64_t)pos);
+        }
+        if (sampled) return (P)(ld_gather<P>(ix.suffix_array + quot) + offset);
+        if (pos == (P)(ix.sentinel_index - 1)) return offset;  // None arm, locate/mod.rs:27-30
+        uint64_t q;
+        uint32_t rem;
+        rank_addr<P, VBITS>(ix, pos, q, rem);
+        Block<NPL, VBITS> b;
+        P ck;
+        uint32_t s;
+        if constexpr (ILV) {
+            const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
+            b.load_aligned(e);
+            s = b.symidx_of(rem);
+            ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
+        } else {
+            b.load(ix.blocks, q);
+            s = b.symidx_of(rem);
+            ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
+        }
+        pos = (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
+        offset += 1;
+    }
+}
+
+// ---- text verification ---------------------------------------------------------------------------------------------
+// Once the SA interval of a pattern's suffix has shrunk to a handful of rows while many symbols are still to come (150 bp
+// reads: after ~16 of 150 symbols on a 1 Gbp text), walking the remaining symbols through the index costs one random
+// cache line per symbol.  The engine keeps a packed copy of the TEXT next to the blob (derived from the blob at load:
+// every SA row's text position comes from locate_row, its BWT symbol precedes that position) and finishes such patterns
+// by locating each candidate row and comparing the unread prefix of the pattern against the text in front of it: two or
+// three sectors instead of a hundred lines.  At most one candidate can then survive in the common case, and the pattern
+// is RESOLVED: count 0, or count 1 with the text position known (no SA row is needed any more).  When two or more
+// candidates survive -- a true repeat of the whole pattern -- the result must come in SA-row order of the full pattern
+// (locate/mod.rs:19), which only the index knows, so the backward search simply continues.  Results are identical either
+// way; tests run with the text copy on and off.
+constexpr uint32_t VERIFY_MAX_ROWS = 4;
+
+__device__ __forceinline__ uint32_t text_symbol(const uint32_t* __restrict__ text, uint32_t bits, uint64_t i) {
+    const uint64_t bit = i * bits;
+    return (__ldg(text + (bit >> 5)) >> (uint32_t)(bit & 31u)) & ((1u << bits) - 1u);
+}
+
+// FmIndex::get_pos_range (locate/with_slice.rs:21-33) for ONE non-empty pattern p[0, len) (stored back to front when
+// `reversed`).  With in_key > 0 the last in_key symbols come out of `key` (see pack_keys_kernel).
 // Seeding: patterns at least ext_m symbols long start from the extended k-mer table (one lookup resolves the last
 // ext_m symbols -- the device twin of the reference's kLTS, count_array.rs:203-233, with a longer k chosen for
 // HBM instead of for a CPU cache); shorter ones use the blob's own kLTS.
 template <class P, int NPL, int VBITS, bool ILV>
+__device__ __forceinline__ void search_pattern(const DevIndex<P>& ix, const uint8_t* p, uint64_t len, bool reversed,
+                                               uint64_t key, uint32_t in_key, uint32_t bits, const uint8_t* s_table,
+                                               const uint8_t* s_rank, const uint8_t* s_lut, const P* s_count, int& errbits,
+                                               P& sp, P& ep, bool& resolved) {
+    const uint32_t S = ix.symbol_count;
+    const uint32_t k = ix.kmer_size;
+    const uint64_t sym_mask = (1ull << bits) - 1;
+    uint64_t pi = 0;
+    sp = 0;
+    ep = 0;
+    // logical (forward) symbol j of the pattern
+    auto sym_at = [&](uint64_t j) -> uint32_t {
+        const uint64_t from_end = len - 1 - j;
+        if (from_end < in_key) return (uint32_t)((key >> (64u - bits * ((uint32_t)from_end + 1))) & sym_mask);
+        uint32_t s = s_table[p[reversed ? from_end : j]];   // plain load: p may point into the staged copy in shared memory
+        if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
+        return s;
+    };
+    if (ix.ext && len >= ix.ext_m) {
+        // extended table: index = trailing ext_m symbols as base-s_eff digits of their rank among the
+        // symbols that occur in the text, first symbol most significant
+        uint64_t e = 0;
+        bool absent = false;
+        for (uint32_t j = 0; j < ix.ext_m; j++) {
+            const uint32_t r = s_rank[sym_at(len - ix.ext_m + j)];
+            absent |= (r == 0xffu);
+            e = e * ix.s_eff + r;
+        }
+        if (!absent) {
+            const P* q = ix.ext + 2 * e;
+            sp = __ldg(q);
+            ep = (P)(sp + __ldg(q + 1));
+        }
+        pi = len - ix.ext_m;
+    } else if (len < k) {
+        // CountArrayView::get_initial_pos_range_and_idx_of_pattern (count_array.rs:203-233)
+        uint64_t start = 0;
+        for (uint64_t j = 0; j < len; j++) start += (uint64_t)(sym_at(j) + 1) * __ldg(ix.kmer_multiplier + j);
+        const uint64_t end = start + __ldg(ix.kmer_multiplier + (len - 1)) - 1;
+        sp = __ldg(ix.kmer_count_table + (start - 1));
+        ep = __ldg(ix.kmer_count_table + end);
+        pi = 0;
+    } else {
+        uint64_t start = 0;
+        for (uint32_t j = 0; j < k; j++) start += (uint64_t)(sym_at(len - k + j) + 1) * __ldg(ix.kmer_multiplier + j);
+        sp = __ldg(ix.kmer_count_table + (start - 1));
+        ep = __ldg(ix.kmer_count_table + start);
+        pi = len - k;
+    }
+    // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
+    resolved = false;
+    bool may_verify = ix.text != nullptr;
+    // accesses one candidate costs: its LF walk to a sampled row ((r-1)/2 steps on average), the SA word, ~2 text sectors
+    const uint64_t verify_cost = (uint64_t)(ix.sampling_ratio - 1) / 2 + 3;
+    uint32_t stalled = 0;
+    for (;;) {
+        // ---- backward steps, until the pattern is finished or text verification should take over.
+        // One more backward step costs ~2 random lines and divides the candidates by the alphabet size on non-repetitive
+        // text, so the search keeps stepping until ONE row is left; a small interval that has stopped shrinking (a repeat)
+        // is verified as it is.  Not worth it when fewer steps are left than it costs.
+        // (The lanes of a warp leave this loop after different numbers of steps and WAIT for each other behind it, so that
+        // the long comparison below runs once per warp -- inside one loop the lanes entered it in different iterations and
+        // the warp executed it four times over: ncu, 150 bp reads, 8.6 active lanes per instruction.)
+        uint64_t rows = 0;
+        bool verify = false;
+        while (sp < ep && pi > 0) {
+            rows = (uint64_t)(ep - sp);
+            verify = may_verify && rows <= VERIFY_MAX_ROWS && (rows == 1 || stalled >= 2) && 2 * pi > rows * verify_cost;
+            if (verify) break;
+            pi -= 1;
+            const uint32_t sy = sym_at(pi);
+            backward_step<P, NPL, VBITS, ILV>(ix, sy, s_count[sy], sp, ep);
+            stalled = (uint64_t)(ep - sp) == rows ? stalled + 1 : 0;
+        }
+        if (!verify) return;
+        // ---- text verification (see above)
+        uint64_t t0[VERIFY_MAX_ROWS];
+        uint32_t alive = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < VERIFY_MAX_ROWS; c++) {
+            t0[c] = 0;
+            if (c < rows) {
+                const P pos = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(sp + c));
+                if ((uint64_t)pos >= pi) { t0[c] = (uint64_t)pos - pi; alive |= 1u << c; }   // else: it would start before the text
+            }
+        }
+        // pattern[0, pi) against the text in front of every candidate, one 32-bit word of packed text per comparison;
+        // the pattern's word is built once and shared by the candidates
+        const uint32_t tb = ix.text_bits, per = 32u / tb;
+        const bool plain = in_key == 0 && !reversed;   // the usual case: symbols straight from the pattern bytes
+        for (uint64_t j0 = 0; j0 < pi && alive; j0 += per) {
+            const uint32_t m = pi - j0 < per ? (uint32_t)(pi - j0) : per;
+            uint32_t code = 0, flags = 0;
+            if (plain) {
+                const uint8_t* q = p + j0;
+                for (uint32_t k2 = 0; k2 < m; k2++) {
+                    const uint32_t v = s_lut[q[k2]];               // rank | 0x80 never occurs | 0x40 PassThrough byte >= S
+                    flags |= v;
+                    code |= (v & ((1u << tb) - 1u)) << (k2 * tb);
+                }
+            } else {
+                for (uint32_t k2 = 0; k2 < m; k2++) {
+                    const uint32_t rk = s_rank[sym_at(j0 + k2)];
+                    flags |= rk & 0x80u;
+                    code |= (rk & ((1u << tb) - 1u)) << (k2 * tb);
+                }
+            }
+            if (flags & 0x40u) errbits |= ERRBIT_BAD_SYMBOL;
+            if (flags & 0x80u) { alive = 0; break; }               // a symbol that never occurs in the text
+            const uint32_t mask = m * tb >= 32u ? 0xffffffffu : (1u << (m * tb)) - 1u;
+#pragma unroll
+            for (uint32_t c = 0; c < VERIFY_MAX_ROWS; c++) {
+                if (alive & (1u << c)) {
+                    const uint64_t bit = (t0[c] + j0) * tb;
+                    const uint32_t* tw = ix.text + (bit >> 5);
+                    const uint32_t have = __funnelshift_r(__ldg(tw), __ldg(tw + 1), (uint32_t)(bit & 31u));   // array is padded
+                    if ((have ^ code) & mask) alive &= ~(1u << c);
+                }
+            }
+        }
+        const uint32_t ok = (uint32_t)__popc(alive);
+        if (ok <= 1) {
+            P okpos = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < VERIFY_MAX_ROWS; c++) if (alive & (1u << c)) okpos = (P)t0[c];
+            sp = okpos;
+            ep = (P)(okpos + ok);
+            resolved = ok == 1;
+            return;
+        }
+        may_verify = false;   // a repeat of the whole pattern: the index decides the order of its rows
+    }
+}
+
+// One pattern per thread, grid-stride.  Work item w handles pattern idx[w] (idx == NULL: identity).  Outputs in WORK
+// order, coalesced.  When the work order is the caller's order, a CTA first copies the bytes of its 256 patterns -- one
+// contiguous range -- into shared memory with coalesced word loads (stage_bytes of dynamic shared memory; ranges that do
+// not fit are read in place): a thread reading its own pattern byte by byte from global memory costs one L1 wavefront per
+// lane and byte, which made 150 bp reads LSU-bound (21 ms per 10^7 reads) once text verification had removed the LF walks.
+template <class P, int NPL, int VBITS, bool ILV>
 __global__ void __launch_bounds__(SEARCH_THREADS)
-search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io) {
+search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io, uint32_t stage_bytes) {
+    extern __shared__ __align__(16) uint8_t s_stage[];
     __shared__ uint8_t s_table[256];
     __shared__ uint8_t s_rank[64];
+    __shared__ uint8_t s_lut[256];   // byte -> rank among the occurring symbols | 0x80 never occurs | 0x40 PassThrough byte >= S
     __shared__ P s_count[65];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = (ix.table && !pb.preencoded) ? ix.table[i] : (uint8_t)i;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t t = (ix.table && !pb.preencoded) ? ix.table[i] : (uint32_t)i;
+        s_table[i] = (uint8_t)t;
+        const uint32_t sidx = t >= ix.symbol_count ? ix.symbol_count - 1 : t;
+        const uint32_t rk = ix.sym_rank[sidx];
+        s_lut[i] = (uint8_t)((rk == 0xffu ? 0x80u : (rk & 0x3fu)) | (t >= ix.symbol_count ? 0x40u : 0u));
+    }
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = ix.sym_rank[i];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     __syncthreads();
 
-    const uint32_t S = ix.symbol_count;
-    const uint32_t k = ix.kmer_size;
     const uint32_t bits = io.bits;
     const uint32_t in_key = io.keys ? 64u / bits : 0u;  // symbols (from the end) available in the key
-    const uint64_t sym_mask = (1ull << bits) - 1;
+    const bool may_stage = stage_bytes >= 64 && !io.idx;
     int errbits = 0;
     unsigned long long rows = 0;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < pb.n; w += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t wb = (uint64_t)blockIdx.x * blockDim.x; wb < pb.n; wb += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t w = wb + threadIdx.x;
+        // ---- stage the byte range of work items [wb, we) when it fits
+        const uint64_t we = wb + blockDim.x < pb.n ? wb + blockDim.x : pb.n;
+        uint64_t b0 = 0, b1 = 0;
+        bool staged = false;
+        uint32_t skew = 0;
+        if (may_stage) {
+            b0 = pb.offs ? pb.offs[wb] : wb * (uint64_t)pb.fixed_len;
+            b1 = pb.offs ? pb.offs[we] : we * (uint64_t)pb.fixed_len;
+            skew = (uint32_t)(reinterpret_cast<uintptr_t>(pb.pats + b0) & 3u);   // keep the word alignment of the source
+            staged = b1 >= b0 && b1 - b0 + skew <= (uint64_t)stage_bytes;
+        }
+        if (may_stage) __syncthreads();   // the previous range is no longer read
+        if (staged) {
+            const uint8_t* src = pb.pats + b0;
+            const uint32_t nbytes = (uint32_t)(b1 - b0);
+            const uint32_t head = nbytes < ((4u - skew) & 3u) ? nbytes : ((4u - skew) & 3u);
+            const uint32_t words = (nbytes - head) >> 2;
+            const uint32_t tail0 = head + (words << 2);
+            if (threadIdx.x < head) s_stage[skew + threadIdx.x] = src[threadIdx.x];
+            const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src + head);
+            uint32_t* dstw = reinterpret_cast<uint32_t*>(s_stage + skew + head);
+            for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dstw[i] = __ldg(srcw + i);
+            if (threadIdx.x < nbytes - tail0) s_stage[skew + tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
+        }
+        if (may_stage) __syncthreads();
+        if (w >= pb.n) continue;
         const uint64_t i = io.idx ? (uint64_t)io.idx[w] : w;
         const uint64_t key = io.keys ? io.keys[w] : 0ull;
-        uint64_t pi = 0;
         P sp = 0, ep = 0;
         uint64_t base, len;
         if (pb.offs) { base = pb.offs[i]; len = pb.offs[i + 1] - base; }
         else { base = i * (uint64_t)pb.fixed_len; len = pb.fixed_len; }
-        const uint8_t* p = pb.pats + base;
-        if (len == 0) {
-            errbits |= ERRBIT_EMPTY_PATTERN;
-        } else {
-            // logical (forward) symbol j of the pattern
-            auto sym_at = [&](uint64_t j) -> uint32_t {
-                const uint64_t from_end = len - 1 - j;
-                if (from_end < in_key) return (uint32_t)((key >> (64u - bits * ((uint32_t)from_end + 1))) & sym_mask);
-                uint32_t s = s_table[__ldg(p + (pb.reversed ? from_end : j))];
-                if (s >= S) { errbits |= ERRBIT_BAD_SYMBOL; s = S - 1; }
-                return s;
-            };
-            if (ix.ext && len >= ix.ext_m) {
-                // extended table: index = trailing ext_m symbols as base-s_eff digits of their rank among the
-                // symbols that occur in the text, first symbol most significant
-                uint64_t e = 0;
-                bool absent = false;
-                for (uint32_t j = 0; j < ix.ext_m; j++) {
-                    const uint32_t r = s_rank[sym_at(len - ix.ext_m + j)];
-                    absent |= (r == 0xffu);
-                    e = e * ix.s_eff + r;
-                }
-                if (!absent) {
-                    const P* q = ix.ext + 2 * e;
-                    sp = __ldg(q);
-                    ep = (P)(sp + __ldg(q + 1));
-                }
-                pi = len - ix.ext_m;
-            } else if (len < k) {
-                // CountArrayView::get_initial_pos_range_and_idx_of_pattern (count_array.rs:203-233)
-                uint64_t start = 0;
-                for (uint64_t j = 0; j < len; j++) start += (uint64_t)(sym_at(j) + 1) * __ldg(ix.kmer_multiplier + j);
-                const uint64_t end = start + __ldg(ix.kmer_multiplier + (len - 1)) - 1;
-                sp = __ldg(ix.kmer_count_table + (start - 1));
-                ep = __ldg(ix.kmer_count_table + end);
-                pi = 0;
-            } else {
-                uint64_t start = 0;
-                for (uint32_t j = 0; j < k; j++) start += (uint64_t)(sym_at(len - k + j) + 1) * __ldg(ix.kmer_multiplier + j);
-                sp = __ldg(ix.kmer_count_table + (start - 1));
-                ep = __ldg(ix.kmer_count_table + start);
-                pi = len - k;
-            }
-            // LF mapping (with_slice.rs:27-31): stops as soon as the interval is empty
-            while (sp < ep && pi > 0) {
-                pi -= 1;
-                { const uint32_t sy = sym_at(pi); backward_step<P, NPL, VBITS, ILV>(ix, sy, s_count[sy], sp, ep); }
-            }
-        }
+        bool resolved = false;
+        const uint8_t* p = staged ? s_stage + skew + (base - b0) : pb.pats + base;
+        if (len == 0) errbits |= ERRBIT_EMPTY_PATTERN;
+        else search_pattern<P, NPL, VBITS, ILV>(ix, p, len, pb.reversed != 0, key, in_key, bits, s_table, s_rank, s_lut, s_count, errbits, sp, ep, resolved);
         const P cnt = (P)(ep - sp);
+        if (io.resolved_out) io.resolved_out[w] = resolved ? 1 : 0;
         if (io.sp_out) io.sp_out[w] = sp;
         if (io.cnt_out) io.cnt_out[w] = cnt;
         if (io.heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(io.heavy_seen, 1ull);  // rare: sizes the heavy list
@@ -258,6 +444,43 @@ static __global__ void ilv_build_kernel(const uint32_t* __restrict__ blocks, uin
         if (w < block_words) v = blocks[q * block_words + w];
         else if (w >= ck_off_words && w < ck_off_words + row_words) v = rows[q * row_words + (w - ck_off_words)];
         dst[t] = v;
+    }
+}
+
+// ---- packed text copy (built once per index at load; "text verification" above) -----------------------------------------
+// Row r of the suffix array: its suffix starts at text position locate_row(r), and the BWT symbol of the row is the text
+// symbol right before it.  One thread per row; the symbol (as its rank among the occurring symbols) is OR-ed into the
+// zeroed packed array.
+template <class P, int NPL, int VBITS, bool ILV>
+__global__ void __launch_bounds__(256)
+text_build_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t* __restrict__ text) {
+    __shared__ P s_count[65];
+    __shared__ uint8_t s_rank[64];
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = ix.sym_rank[i];
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // the last text symbol precedes the sentinel: it is the BWT symbol of the `$` row, which the sentinel-free row
+        // numbering skips -- stored BWT index 0 (bwm/mod.rs:107-108, crate_bio_manual/mod.rs:14-24)
+        Block<NPL, VBITS> b;
+        if constexpr (ILV) b.load_aligned(ix.ilv);
+        else b.load(ix.blocks, (uint64_t)0);
+        const uint64_t bit = (n - 1) * bits;
+        atomicOr(text + (bit >> 5), (uint32_t)s_rank[b.symidx_of(0)] << (uint32_t)(bit & 31u));
+    }
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        if ((P)r == (P)(ix.sentinel_index - 1)) continue;   // the row whose BWT symbol is the sentinel: nothing precedes text[0]
+        uint64_t q;
+        uint32_t rem;
+        rank_addr<P, VBITS>(ix, (P)r, q, rem);
+        Block<NPL, VBITS> b;
+        if constexpr (ILV) b.load_aligned(ix.ilv + q * ix.ilv_stride);
+        else b.load(ix.blocks, q);
+        const uint32_t sym = b.symidx_of(rem);
+        const P pos = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)r);
+        if (pos == 0) continue;
+        const uint64_t bit = ((uint64_t)pos - 1) * bits;
+        atomicOr(text + (bit >> 5), (uint32_t)s_rank[sym] << (uint32_t)(bit & 31u));
     }
 }
 
@@ -811,44 +1034,54 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     }
 }
 
-// FmIndex::write_locations_to_buffer (locate/mod.rs:14-37) for ONE SA row: LF-walk to the nearest
-// sampled row (BwmView::get_pre_rank_and_symidx, bwm/mod.rs:217-236), then
-// SuffixArrayView::get_location_of (suffix_array/mod.rs:100-105).
+// ---- small batches (a few thousand patterns at most; every single-pattern call) -------------------------------------
+// ONE launch does search and locate: a thread takes one pattern, runs the backward search and walks up to `slots_per` of
+// its SA rows into a fixed slot array; the host turns counts + slots into the CSR result (or, when some pattern has more
+// rows than slots, runs the general pipeline).  Patterns, counts, slots and the status word live in PINNED HOST memory
+// mapped into the device address space, so the call is one kernel launch and one stream synchronisation -- no copy calls,
+// no memsets: what a latency-bound single `count` / `locate` needs (round 1: 43 / 78 us per call, six runtime calls each).
+struct SmallOut {
+    void* cnt;        // P[n]
+    void* slots;      // P[n * slots_per], NULL for count
+    uint32_t slots_per;
+    uint8_t* status;  // u8[n]: error bits of every pattern
+};
 template <class P, int NPL, int VBITS, bool ILV>
-__device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restrict__ s_count, P pos) {
-    P offset = 0;
-    for (;;) {
-        // pos % sampling_ratio != 0
-        uint64_t quot;
-        bool sampled;
-        if (ix.ratio_mask != 0xffffffffu) {
-            sampled = ((uint32_t)pos & ix.ratio_mask) == 0;
-            quot = (uint64_t)pos >> ix.ratio_shift;
-        } else {
-            quot = (uint64_t)pos / ix.sampling_ratio;
-            sampled = (quot * ix.sampling_ratio == (uint64_t)pos);
-        }
-        if (sampled) return (P)(ld_gather<P>(ix.suffix_array + quot) + offset);
-        if (pos == (P)(ix.sentinel_index - 1)) return offset;  // None arm, locate/mod.rs:27-30
-        uint64_t q;
-        uint32_t rem;
-        rank_addr<P, VBITS>(ix, pos, q, rem);
-        Block<NPL, VBITS> b;
-        P ck;
-        uint32_t s;
-        if constexpr (ILV) {
-            const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
-            b.load_aligned(e);
-            s = b.symidx_of(rem);
-            ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
-        } else {
-            b.load(ix.blocks, q);
-            s = b.symidx_of(rem);
-            ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
-        }
-        pos = (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
-        offset += 1;
+__global__ void __launch_bounds__(128)
+small_batch_kernel(const DevIndex<P> ix, const PatternBatch pb, const SmallOut out) {
+    __shared__ uint8_t s_table[256];
+    __shared__ uint8_t s_rank[64];
+    __shared__ uint8_t s_lut[256];   // byte -> rank among the occurring symbols | 0x80 never occurs | 0x40 PassThrough byte >= S
+    __shared__ P s_count[65];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t t = (ix.table && !pb.preencoded) ? ix.table[i] : (uint32_t)i;
+        s_table[i] = (uint8_t)t;
+        const uint32_t sidx = t >= ix.symbol_count ? ix.symbol_count - 1 : t;
+        const uint32_t rk = ix.sym_rank[sidx];
+        s_lut[i] = (uint8_t)((rk == 0xffu ? 0x80u : (rk & 0x3fu)) | (t >= ix.symbol_count ? 0x40u : 0u));
     }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = ix.sym_rank[i];
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pb.n) return;
+    int errbits = 0;
+    P sp = 0, ep = 0;
+    uint64_t base, len;
+    if (pb.offs) { base = pb.offs[i]; len = pb.offs[i + 1] - base; }
+    else { base = i * (uint64_t)pb.fixed_len; len = pb.fixed_len; }
+    bool resolved = false;
+    if (len == 0) errbits |= ERRBIT_EMPTY_PATTERN;
+    else search_pattern<P, NPL, VBITS, ILV>(ix, pb.pats + base, len, pb.reversed != 0, 0ull, 0u, 1u, s_table, s_rank, s_lut, s_count, errbits, sp, ep, resolved);
+    const P cnt = (P)(ep - sp);
+    reinterpret_cast<P*>(out.cnt)[i] = cnt;
+    if (out.slots) {
+        P* slot = reinterpret_cast<P*>(out.slots) + i * out.slots_per;
+        const uint32_t rows = (uint64_t)cnt < out.slots_per ? (uint32_t)cnt : out.slots_per;
+        if (resolved) slot[0] = sp;   // text verification: the position itself
+        else for (uint32_t j = 0; j < rows; j++) slot[j] = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(sp + j));
+    }
+    out.status[i] = (uint8_t)errbits;
 }
 
 constexpr int LOCATE_THREADS = 256;
@@ -895,7 +1128,8 @@ template <class P, int NPL, int VBITS, bool ILV, bool BUCKET>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
                    const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
-                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy, BucketOut<P> bk) {
+                   P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy, BucketOut<P> bk,
+                   const uint8_t* __restrict__ resolved) {
     __shared__ P s_count[65];
     for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
     __syncthreads();
@@ -909,10 +1143,12 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
         P sp = 0;
         uint64_t obase = 0;
         uint32_t pat = 0;
+        bool res = false;   // sp is the text position already (text verification)
         if (w < n) {
             const P cw = cnt_work[w];
             if (cw != 0) {
                 sp = sp_work[w];
+                res = resolved && resolved[w];
                 pat = idx ? idx[w] : (uint32_t)w;
                 if constexpr (BUCKET) obase = atomicAdd(bk.cursor + (pat >> SB_SHIFT), (unsigned long long)cw);
                 else obase = offs[w];
@@ -938,7 +1174,7 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
         };
         if (__all_sync(full, c <= 1u)) {
             // common case: at most one row per pattern, no redistribution needed
-            if (c) emit(obase, locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp), pat);
+            if (c) emit(obase, res ? sp : locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp), pat);
             continue;
         }
         uint32_t incl = c;
@@ -963,9 +1199,10 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
             const P osp = __shfl_sync(full, sp, o);
             const uint64_t oo = __shfl_sync(full, obase, o);
             const uint32_t opat = __shfl_sync(full, pat, o);
+            const bool ores = __shfl_sync(full, (int)res, o) != 0;
             if (r < total) {
                 const uint32_t j = r - e;
-                emit(oo + j, locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j)), opat);
+                emit(oo + j, ores ? osp : locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j)), opat);
             }
         }
     }

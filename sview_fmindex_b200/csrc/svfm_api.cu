@@ -68,6 +68,7 @@ static int finish_load(svfm_index* ix) {
 
 static int build_ext_table(svfm_index* ix);
 static int build_ilv_table(svfm_index* ix);
+static int build_text_copy(svfm_index* ix);
 
 static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int device, bool src_on_device,
                        svfm_index** out, uint64_t err_detail[2]) {
@@ -113,7 +114,9 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
     rc = finish_load(ix);
     if (rc == SVFM_OK) rc = build_ext_table(ix);
     if (rc == SVFM_OK) rc = build_ilv_table(ix);
+    if (rc == SVFM_OK) rc = build_text_copy(ix);
     if (rc) {
+        if (ix->d_text) cudaFree(ix->d_text);
         if (ix->d_ilv) cudaFree(ix->d_ilv);
         if (ix->d_ext) cudaFree(ix->d_ext);
         cudaFree(ix->d_alloc);
@@ -136,6 +139,15 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(uint64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess && ix->l2_window_bytes) {
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.base_ptr = ix->d_ext;
+        v.accessPolicyWindow.num_bytes = ix->l2_window_bytes;
+        v.accessPolicyWindow.hitRatio = 1.0f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) (void)cudaGetLastError();
+    }
     if (e != cudaSuccess) {
         g_last_error = std::string("session_new: ") + cudaGetErrorString(e);
         (void)cudaGetLastError();
@@ -155,6 +167,7 @@ static void session_delete(svfm_session* s) {
     if (s->d_err) cudaFree(s->d_err);
     if (s->d_counters) cudaFree(s->d_counters);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_small) cudaFreeHost(s->h_small);
     collect_spans(s);
     for (cudaEvent_t e : s->free_events) cudaEventDestroy(e);
     delete s;
@@ -260,7 +273,14 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
         uint32_t t = t_env ? t_env : 6u / p.bits;
         while (t > 1 && p.bits * t > 9) t--;
         p.steps_per_round = t < 1 ? 1 : t;
-        return p;
+        // With the packed text copy the generic kernel finishes a pattern by text verification as soon as its interval is
+        // down to a few rows, whatever is left of it; the sweep search still walks every symbol, one partition round per
+        // steps_per_round symbols.  Measured on B200: the sweep wins while it needs at most 2 rounds (20-mers on 1 Gbp DNA:
+        // 2 rounds), the generic kernel beyond (32-mers on 3.1 Gbp: 6 rounds, 12-mer proteins: 6 rounds of one step).
+        static const uint32_t max_rounds_env = [] { const char* e = std::getenv("SVFM_SWEEP_MAX_ROUNDS"); return e ? (uint32_t)atoi(e) : 2u; }();
+        const uint32_t rounds = (pb.fixed_len - ix->ext_m + p.steps_per_round - 1) / p.steps_per_round;
+        if (ix->d_text && sweep_min_patterns(ix) != 0 && rounds > max_rounds_env) { p.sweep = false; p.bits = (uint32_t)bits_for(S) ? (uint32_t)bits_for(S) : 1u; }
+        else return p;
     }
     if (n < sort_min_patterns(ix)) return p;
     // Sort on as many trailing symbols as it takes to tell the occ blocks apart: log_{S_eff}(blocks) + 1
@@ -279,8 +299,9 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
 static int run_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, const uint64_t** keys_out,
                        const uint32_t** idx_out) {
     int rc;
-    if ((rc = s->keys0.reserve(pb.n * 8)) || (rc = s->keys1.reserve(pb.n * 8)) || (rc = s->vals0.reserve(pb.n * 4)) ||
-        (rc = s->vals1.reserve(pb.n * 4)))
+    const uint64_t rn = rsv(s, pb.n);
+    if ((rc = s->keys0.reserve(rn * 8)) || (rc = s->keys1.reserve(rn * 8)) || (rc = s->vals0.reserve(rn * 4)) ||
+        (rc = s->vals1.reserve(rn * 4)))
         return rc;
     cub::DoubleBuffer<uint64_t> keys((uint64_t*)s->keys0.ptr, (uint64_t*)s->keys1.ptr);
     cub::DoubleBuffer<uint32_t> vals((uint32_t*)s->vals0.ptr, (uint32_t*)s->vals1.ptr);
@@ -380,17 +401,21 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     const uint32_t len = pb.fixed_len, bits = plan.bits;
     const uint32_t digit_bits = bits * plan.steps_per_round, nb_max = 1u << digit_bits;
     int rc;
-    if ((rc = s->keys0.reserve(n * 4)) || (rc = s->keys1.reserve(n * 4)) || (rc = s->pay0.reserve(n * sizeof(Pay))) ||
-        (rc = s->pay1.reserve(n * sizeof(Pay))) || (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + rounds + 64) * 4)))
+    const uint64_t rn = rsv(s, n);
+    if ((rc = s->keys0.reserve(rn * 4)) || (rc = s->keys1.reserve(rn * 4)) || (rc = s->pay0.reserve(rn * sizeof(Pay))) ||
+        (rc = s->pay1.reserve(rn * sizeof(Pay))) || (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + rounds + 64) * 4)))
         return rc;
     cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
     cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
     uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
     size_t t1 = 0;
-    // Only the top 24 bits of the table index are sorted (three radix passes): items that differ in the lower bits only
-    // sit in neighbouring table entries and SA rows (a 2^28-entry DNA table: 16 entries = ~60 rows, one occ block), so
-    // leaving them unordered costs no locality, and correctness never depends on the order.
-    const int sort_begin = plan.prefix_bits > 24 ? plan.prefix_bits - 24 : 0;
+    // Only the top 16 bits of the table index are sorted (two radix passes).  Items that differ in the lower bits only sit
+    // within 1/65536 of the SA (a 2^28-entry DNA table on 1 Gbp: 4096 entries, ~240 occ blocks = 10 KB of index data, which
+    // the CTAs working on that stretch share through L1/L2), and correctness never depends on the order.  Measured on B200,
+    // 10^8 20-mers: 28 bits (4 passes) and 24 bits (3 passes) give the same round times; 16 bits make the first round
+    // 0.6 ms slower and the sort 0.85 ms shorter (14.65 against 14.87 ms per batch); SVFM_PRESORT_BITS overrides.
+    static const int sort_bits = [] { const char* e = std::getenv("SVFM_PRESORT_BITS"); return e ? atoi(e) : 16; }();
+    const int sort_begin = plan.prefix_bits > sort_bits ? plan.prefix_bits - sort_bits : 0;
     SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, sort_begin, plan.prefix_bits, s->stream));
     if ((rc = s->cub_temp.reserve(t1))) return rc;
     int sms = 148;
@@ -436,9 +461,9 @@ static const TypeOps* type_ops(const svfm_type& t) {
 #define SVFM_BY_POS(FN, ...) (s->ix->type.pos_bits == 32 ? FN<uint32_t>(__VA_ARGS__) : FN<uint64_t>(__VA_ARGS__))
 
 static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64_t* keys, const uint32_t* idx, uint32_t bits,
-                           void* d_sp_work, void* d_cnt_work, const SbOut& sb = SbOut{}) {
+                           void* d_sp_work, void* d_cnt_work, const SbOut& sb = SbOut{}, uint8_t* d_resolved = nullptr) {
     const TypeOps* ops = type_ops(s->ix->type);
-    return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb) : SVFM_ERR_BAD_TYPE;
+    return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb, d_resolved) : SVFM_ERR_BAD_TYPE;
 }
 static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode, void* d_sp_work,
                                  void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb = SbOut{}) {
@@ -474,16 +499,50 @@ static int build_ilv_table(svfm_index* ix) {
     ix->ilv_ck_off = (uint32_t)ck_off;
     return SVFM_OK;
 }
+static std::atomic<uint64_t> g_l2_persist{[] {  // extended tables up to this many bytes get an L2 persisting window (0 = never)
+    const char* e = std::getenv("SVFM_L2_PERSIST");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(64u << 20);
+}()};
 static int build_ext_table(svfm_index* ix) {
     const TypeOps* ops = type_ops(ix->type);
-    return ops ? ops->build_ext(ix->type.planes, ix, ext_bits_for(ix)) : SVFM_ERR_BAD_TYPE;
+    if (!ops) return SVFM_ERR_BAD_TYPE;
+    int rc = ops->build_ext(ix->type.planes, ix, ext_bits_for(ix));
+    if (rc) return rc;
+    // north_star: "the k-mer table is staged in shared memory or an L2-persisting window".  The default table (2^28 entries,
+    // 2 GiB) is far larger than L2 and is read once per pattern, so nothing is pinned for it; a table of at most 64 MiB
+    // (SVFM_TUNE_EXT_BITS <= 23 for 32-bit positions: memory-constrained deployments) is marked persisting in L2 for every
+    // kernel of every session of this index (cudaAccessPolicyWindow, set per stream in session_new).
+    const uint64_t bytes = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
+    int max_persist = 0, max_window = 0;
+    if (bytes && bytes <= g_l2_persist.load() &&
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device) == cudaSuccess &&
+        bytes <= (uint64_t)max_persist && bytes <= (uint64_t)max_window) {
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < bytes &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) != cudaSuccess)
+            (void)cudaGetLastError();
+        else
+            ix->l2_window_bytes = bytes;
+    }
+    (void)cudaGetLastError();
+    return SVFM_OK;
+}
+static std::atomic<uint64_t> g_text{[] {  // build the packed text copy at load (text verification, search_kernels.cuh)
+    const char* e = std::getenv("SVFM_TEXT");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
+}()};
+static int build_text_copy(svfm_index* ix) {
+    if (!g_text.load()) return SVFM_OK;
+    const TypeOps* ops = type_ops(ix->type);
+    return ops ? ops->build_text(ix->type.planes, ix) : SVFM_ERR_BAD_TYPE;
 }
 static int dispatch_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
                            const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
-                           void* d_recs = nullptr, unsigned long long* d_cursor = nullptr) {
+                           void* d_recs = nullptr, unsigned long long* d_cursor = nullptr, const uint8_t* d_resolved = nullptr) {
     const TypeOps* ops = type_ops(s->ix->type);
     return ops ? ops->locate(s->ix->type.planes, s, n, idx, d_sp_work, d_cnt_work, d_offs, total, heavy_seen, d_positions, d_rec_key,
-                             d_recs, d_cursor)
+                             d_recs, d_cursor, d_resolved)
                : SVFM_ERR_BAD_TYPE;
 }
 // Bucketed sort-back, second half (search_kernels.cuh): CSR offsets + final place of every record, one CTA per bucket.
@@ -537,9 +596,9 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
     int rc;
-    if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
+    if ((rc = s->cnt.reserve((rsv(s, pb.n) + 1) * P))) return rc;
     if (plan.sweep) {
-        if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
+        if ((rc = s->sp.reserve((rsv(s, pb.n) + 1) * P))) return rc;
         const bool by_index = g_bucket_sortback.load() != 0;
         if ((rc = dispatch_search_sweep(s, pb, plan, by_index ? PART_INDEX : PART_NONE, s->sp.ptr, s->cnt.ptr, &idx))) return rc;
         if (by_index) return SVFM_BY_POS(run_scatter_counts, s, pb.n, idx, s->cnt.ptr, d_counts_out);
@@ -564,8 +623,9 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     int rc;
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
     SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
-    if ((rc = s->sp.reserve((pb.n + 1) * P))) return rc;
-    if ((rc = s->cnt.reserve((pb.n + 1) * P))) return rc;
+    const uint64_t rn = rsv(s, pb.n);
+    if ((rc = s->sp.reserve((rn + 1) * P))) return rc;
+    if ((rc = s->cnt.reserve((rn + 1) * P))) return rc;
     const SortPlan plan = plan_sort(s->ix, pb.n, pb);
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
@@ -575,8 +635,10 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     bool bucket = reordered && !by_position && g_bucket_sortback.load() != 0;
     const uint64_t nb = (pb.n + SB_BUCKET - 1) >> SB_SHIFT;
     SbOut sb{};
+    uint8_t* d_resolved = nullptr;
     if (bucket) {
-        if ((rc = s->sb_hist.reserve(nb * 4)) || (rc = s->sb_base.reserve((nb + 1) * 8)) || (rc = s->sb_cursor.reserve(nb * 8))) return rc;
+        const uint64_t rnb = (rn + SB_BUCKET - 1) >> SB_SHIFT;
+        if ((rc = s->sb_hist.reserve(rnb * 4)) || (rc = s->sb_base.reserve((rnb + 1) * 8)) || (rc = s->sb_cursor.reserve(rnb * 8))) return rc;
         sb.hist = (uint32_t*)s->sb_hist.ptr;
         sb.total = s->d_counters + 2;
         SVFM_CUDA(cudaMemsetAsync(sb.hist, 0, nb * 4, s->stream));
@@ -587,7 +649,11 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
             return rc;
     } else {
         if (plan.sorted && (rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
-        if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr, sb))) return rc;
+        if (s->ix->d_text) {  // text verification: the search may hand back text positions instead of SA rows
+            if ((rc = s->resolved.reserve(rn))) return rc;
+            d_resolved = (uint8_t*)s->resolved.ptr;
+        }
+        if ((rc = dispatch_search(s, pb, keys, idx, plan.sorted ? plan.bits : 1, s->sp.ptr, s->cnt.ptr, sb, d_resolved))) return rc;
     }
     if (bucket) {
         {
@@ -605,10 +671,12 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         *total_out = total;
         if (total < 0xffffffffull) {  // the 32-bit bucket counters did not wrap
             const uint64_t rec_bytes = P == 4 ? 8 : 16;
-            if ((rc = s->positions.reserve((total + 1) * P)) || (rc = s->sb_recs.reserve((total + 1) * rec_bytes))) return rc;
+            if ((rc = s->positions.reserve((std::max(total, s->reserve_n) + 1) * P)) ||
+                (rc = s->sb_recs.reserve((std::max(total, s->reserve_n) + 1) * rec_bytes)))
+                return rc;
             *d_positions = s->positions.ptr;
             if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, nullptr, total, heavy_seen, nullptr, nullptr, s->sb_recs.ptr,
-                                      (unsigned long long*)s->sb_cursor.ptr)))
+                                      (unsigned long long*)s->sb_cursor.ptr, d_resolved)))
                 return rc;
             return SVFM_BY_POS(run_sb_place, s, pb.n, nb, d_out_offs, offs32, s->positions.ptr);
         }
@@ -616,12 +684,12 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     }
     uint64_t* offs_final = (uint64_t*)d_out_offs;  // u64 CSR offsets in the caller's order
     if (offs32) {
-        if ((rc = s->offs64.reserve((pb.n + 1) * 8))) return rc;
+        if ((rc = s->offs64.reserve((rn + 1) * 8))) return rc;
         offs_final = (uint64_t*)s->offs64.ptr;
     }
     uint64_t* offs_work = offs_final;  // small batch: work order == caller order
     if (reordered) {
-        if ((rc = s->woffs.reserve((pb.n + 1) * 8))) return rc;
+        if ((rc = s->woffs.reserve((rn + 1) * 8))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
     }
     if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
@@ -634,12 +702,12 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     const uint64_t heavy_seen = s->h_pinned[3];
     *total_out = total;
     if (offs32 && total > 0xffffffffull) return SVFM_ERR_TOO_LARGE;
-    if ((rc = s->positions.reserve((total + 1) * P))) return rc;
+    if ((rc = s->positions.reserve((std::max(total, s->reserve_n) + 1) * P))) return rc;
     const bool records = reordered || by_position;
     if (records && (rc = s->rec_key.reserve((total + 1) * 4))) return rc;
     *d_positions = s->positions.ptr;
     if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, offs_work, total, heavy_seen, s->positions.ptr,
-                              records ? (uint32_t*)s->rec_key.ptr : nullptr)))
+                              records ? (uint32_t*)s->rec_key.ptr : nullptr, nullptr, nullptr, d_resolved)))
         return rc;
     if (records && (rc = dispatch_sortback_records(s, pb.n, total, by_position, reordered, offs_final, d_positions))) return rc;
     if (offs32) {
@@ -675,7 +743,7 @@ static int check_host_patterns(const uint8_t* pats, const uint64_t* offs, uint64
 // ---------------------------------------------------------------------------------------------
 static std::atomic<uint64_t> g_chunk_patterns{[] {
     const char* e = std::getenv("SVFM_CHUNK");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(8u << 20);
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
 static std::atomic<uint64_t> g_host_workers{[] {
     const char* e = std::getenv("SVFM_WORKERS");
@@ -725,16 +793,22 @@ struct ChunkPlan {
     std::vector<uint64_t> bounds;  // chunks + 1 pattern indices
     uint64_t begin(uint64_t c) const { return bounds[c]; }
     uint64_t end(uint64_t c) const { return bounds[c + 1]; }
+    uint64_t largest() const { uint64_t m = 0; for (uint64_t c = 0; c < chunks; c++) m = std::max(m, end(c) - begin(c)); return m; }
 };
 
 // Even chunks of about SVFM_TUNE_CHUNK patterns, every boundary a multiple of 256 patterns (chunk copies stay 16-byte
 // aligned for the TMA staging).  The LAST chunk is halved repeatedly (down to ~1 Mi patterns): the upload stream is the
 // bottleneck of a host batch, so what remains after the last byte has arrived -- kernels + download of the final
 // chunk -- should be small.
-static ChunkPlan plan_chunks(uint64_t n) {
+// AUTO: 8 Mi patterns when the upload is what bounds the call (byte patterns: 20 B each at PCIe speed), 16 Mi when the
+// patterns arrive packed (<= 8 B each): the chunks are then large enough for the sweep search, and the device pipeline, not
+// the bus, is the bottleneck (measured on 10^8 20-mers: packed 2.68 / 3.45 / 2.62 G patterns/s with 8 / 16 / 32 Mi chunks,
+// byte patterns 2.24 / 2.10 / 2.03).
+static ChunkPlan plan_chunks(uint64_t n, uint64_t bytes_per_pattern = 0) {
     ChunkPlan p;
     p.n = n;
     uint64_t c = g_chunk_patterns.load();
+    if (c == (uint64_t)SVFM_TUNE_AUTO) c = (bytes_per_pattern && bytes_per_pattern <= 8) ? (16u << 20) : (8u << 20);
     if (c == 0) c = n;
     uint64_t k = (n + c - 1) / c;
     if (k == 0) k = 1;
@@ -891,7 +965,7 @@ static int begin_group(svfm_uploader* u, const ChunkPlan& cp, const uint8_t* pat
 // per_chunk(session, c) for c in [c0, c1) over up to `workers` sessions; `prologue` runs on the calling thread before it
 // turns into a worker itself.
 template <class Fn, class Pro>
-static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, Fn&& per_chunk, Pro&& prologue) {
+static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, uint64_t reserve_n, Fn&& per_chunk, Pro&& prologue) {
     const uint64_t chunks = c1 - c0;
     const uint64_t hw = g_host_workers.load() ? g_host_workers.load() : 1;
     const int workers = (int)(chunks < hw ? chunks : hw);
@@ -902,6 +976,7 @@ static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, Fn&& per_chunk,
     auto body = [&]() {
         SessionLease lease(ix);
         int rc = lease.acquire();
+        if (lease.s) lease.s->reserve_n = reserve_n;
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= c1) break;
@@ -916,7 +991,7 @@ static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, Fn&& per_chunk,
             }
             if (!run || rc != SVFM_OK) per_chunk(nullptr, c);  // publish "nothing": nobody may wait on this chunk forever
         }
-        if (lease.s) cudaStreamSynchronize(lease.s->stream);
+        if (lease.s) { cudaStreamSynchronize(lease.s->stream); lease.s->reserve_n = 0; }
     };
     if (workers <= 1) {
         prologue();
@@ -954,6 +1029,59 @@ static int upload_direct(svfm_session* s, const uint8_t* pats, const uint64_t* o
     return SVFM_OK;
 }
 
+// ---- small batches: one kernel launch + one synchronisation per call (search_kernels.cuh, small_batch_kernel) --------
+// Arena layout (mapped pinned host memory, allocated on a session's first small call):
+//   [0, 256 KiB) pattern bytes | offsets u64[4097] | counts P[4096] | slots P[4096 * 8] | status u8[4096]
+constexpr uint64_t SMALL_OFF_OFFS = SMALL_MAX_BYTES;
+constexpr uint64_t SMALL_OFF_CNT = SMALL_OFF_OFFS + (SMALL_MAX_PATTERNS + 1) * 8;
+constexpr uint64_t SMALL_OFF_SLOTS = SMALL_OFF_CNT + SMALL_MAX_PATTERNS * 8;
+constexpr uint64_t SMALL_OFF_STATUS = SMALL_OFF_SLOTS + SMALL_MAX_PATTERNS * SMALL_SLOTS * 8;
+constexpr uint64_t SMALL_ARENA = SMALL_OFF_STATUS + SMALL_MAX_PATTERNS;
+static std::atomic<uint64_t> g_small_max{[] {  // batches up to this many patterns take the one-launch path (0 = never)
+    const char* e = std::getenv("SVFM_SMALL_MAX");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : SMALL_MAX_PATTERNS;
+}()};
+static bool small_eligible(uint64_t n, uint64_t bytes, uint32_t flags) {
+    const uint64_t lim = std::min<uint64_t>(g_small_max.load(), SMALL_MAX_PATTERNS);
+    return n > 0 && n <= lim && bytes <= SMALL_MAX_BYTES;
+}
+// Runs the kernel and waits.  want_slots: locate.  Returns the arena through *arena.
+static int small_run(svfm_session* s, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len, uint32_t flags,
+                     bool want_slots, bool preencoded, uint8_t** arena) {
+    if (!s->h_small) {
+        SVFM_CUDA(cudaHostAlloc((void**)&s->h_small, SMALL_ARENA, cudaHostAllocMapped));
+    }
+    uint8_t* a = s->h_small;
+    const uint64_t first = offs ? offs[0] : 0;
+    const uint64_t bytes = offs ? offs[n] - first : n * (uint64_t)fixed_len;
+    std::memcpy(a, pats + first, bytes);
+    PatternBatch pb;
+    pb.pats = a - first;  // offsets stay absolute (the mapped arena has the same address on host and device under UVA)
+    pb.offs = nullptr;
+    if (offs) {
+        std::memcpy(a + SMALL_OFF_OFFS, offs, (n + 1) * 8);
+        pb.offs = reinterpret_cast<const uint64_t*>(a + SMALL_OFF_OFFS);
+    }
+    pb.n = n;
+    pb.fixed_len = fixed_len;
+    pb.reversed = (flags & SVFM_REVERSED) ? 1u : 0u;
+    pb.preencoded = preencoded ? 1u : 0u;
+    SmallOut out;
+    out.cnt = a + SMALL_OFF_CNT;
+    out.slots = want_slots ? a + SMALL_OFF_SLOTS : nullptr;
+    out.slots_per = SMALL_SLOTS;
+    out.status = a + SMALL_OFF_STATUS;
+    const TypeOps* ops = type_ops(s->ix->type);
+    if (!ops) return SVFM_ERR_BAD_TYPE;
+    int rc = ops->small(s->ix->type.planes, s, pb, out);
+    if (rc) return rc;
+    SVFM_CUDA(cudaStreamSynchronize(s->stream));
+    int bits = 0;
+    for (uint64_t i = 0; i < n; i++) bits |= a[SMALL_OFF_STATUS + i];
+    *arena = a;
+    return err_from_bits(bits);
+}
+
 // Packed entry points: the host buffer holds `bpp` bytes per pattern (what the upload machinery sees as fixed_len); each
 // chunk is expanded on the device to one symbol index per byte before the usual pipeline runs on it.
 struct PackedSpec {
@@ -964,7 +1092,7 @@ static int unpack_chunk(svfm_session* s, const PackedSpec& spec, PatternBatch& p
     if (!spec.bits) return SVFM_OK;
     const uint64_t bytes = pb.n * (uint64_t)spec.len;
     int rc;
-    if ((rc = s->unpacked.reserve(bytes + 256))) return rc;
+    if ((rc = s->unpacked.reserve(rsv(s, pb.n) * (uint64_t)spec.len + 256))) return rc;
     PhaseTimer pt(s, SVFM_PHASE_PRESORT, 1);
     unpack_patterns_kernel<<<grid_for((bytes + 3) / 4, 256, s->ix->device), 256, 0, s->stream>>>(pb.pats, pb.n, spec.len, spec.bits, pb.fixed_len,
                                                                                              (uint8_t*)s->unpacked.ptr);
@@ -978,12 +1106,18 @@ static int unpack_chunk(svfm_session* s, const PackedSpec& spec, PatternBatch& p
 static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t n, uint32_t fixed_len,
                       uint32_t flags, void* counts_out, const PackedSpec& spec = PackedSpec()) {
     const uint64_t P = ix->type.pos_bits / 8;
-    const ChunkPlan cp = plan_chunks(n);
+    const ChunkPlan cp = plan_chunks(n, offs ? 0 : fixed_len);
     if (cp.chunks == 1) {
         SessionLease lease(ix);
         int r = lease.acquire();
         if (r) return r;
         svfm_session* s = lease.s;
+        if (!spec.bits && small_eligible(n, offs ? offs[n] - offs[0] : n * (uint64_t)fixed_len, flags)) {
+            uint8_t* a = nullptr;
+            if ((r = small_run(s, pats, offs, n, fixed_len, flags, false, false, &a))) return r;
+            std::memcpy(counts_out, a + SMALL_OFF_CNT, n * P);
+            return SVFM_OK;
+        }
         PatternBatch pb;
         if ((r = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return r;
         if ((r = unpack_chunk(s, spec, pb))) return r;
@@ -1000,14 +1134,14 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
     for (uint64_t g0 = 0; g0 < cp.chunks;) {
         UploadGroup g;
         if ((rc = begin_group(up.u, cp, pats, offs, fixed_len, flags, g0, g))) return rc;
-        rc = run_workers(ix, g.g0, g.g1, [&](svfm_session* s, uint64_t c) -> int {
+        rc = run_workers(ix, g.g0, g.g1, cp.largest(), [&](svfm_session* s, uint64_t c) -> int {
             if (!s) return SVFM_OK;
             const uint64_t a = cp.begin(c), b = cp.end(c);
             PatternBatch pb;
             int r;
             if ((r = await_chunk(s, cp, g, c, pb))) return r;
             if ((r = unpack_chunk(s, spec, pb))) return r;
-            if ((r = s->counts_out.reserve((b - a) * P))) return r;  // not s->cnt: count_device uses that in work order
+            if ((r = s->counts_out.reserve(rsv(s, b - a) * P))) return r;  // not s->cnt: count_device uses that in work order
             if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
             SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
             SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -1035,11 +1169,53 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
     if (o32) static_cast<uint32_t*>(out_offs)[0] = 0; else static_cast<uint64_t*>(out_offs)[0] = 0;
     if (n == 0) return SVFM_OK;
     const uint64_t P = ix->type.pos_bits / 8;
-    const ChunkPlan cp = plan_chunks(n);
+    const ChunkPlan cp = plan_chunks(n, offs ? 0 : fixed_len);
     if (cp.chunks == 1) {  // no upload stream, no worker threads
         SessionLease lease(ix);
         if ((rc = lease.acquire())) return rc;
         svfm_session* s = lease.s;
+        if (!spec.bits && small_eligible(n, bytes, flags)) {
+            uint8_t* a = nullptr;
+            if ((rc = small_run(s, pats, offs, n, fixed_len, flags, true, false, &a))) return rc;
+            // counts + fixed slots -> CSR; a pattern with more rows than slots sends the batch through the general pipeline
+            uint64_t total = 0;
+            bool fits_slots = true;
+            auto count_of = [&](uint64_t i) -> uint64_t {
+                return P == 4 ? (uint64_t)reinterpret_cast<const uint32_t*>(a + SMALL_OFF_CNT)[i] : reinterpret_cast<const uint64_t*>(a + SMALL_OFF_CNT)[i];
+            };
+            for (uint64_t i = 0; i < n; i++) {
+                const uint64_t c = count_of(i);
+                fits_slots &= c <= SMALL_SLOTS;
+                total += c;
+            }
+            if (fits_slots) {
+                if (o32 && total > 0xffffffffull) return SVFM_ERR_TOO_LARGE;
+                *total_out = total;
+                uint64_t at = 0;
+                for (uint64_t i = 0; i <= n; i++) {
+                    if (o32) static_cast<uint32_t*>(out_offs)[i] = (uint32_t)at; else static_cast<uint64_t*>(out_offs)[i] = at;
+                    if (i < n) at += count_of(i);
+                }
+                void* dst = positions;
+                if (alloc_out && total && !(dst = result_alloc(total * P))) return SVFM_ERR_NOMEM;
+                const bool fits = alloc_out || total <= capacity;
+                if (fits && total) {
+                    uint8_t* w = static_cast<uint8_t*>(dst);
+                    for (uint64_t i = 0; i < n; i++) {
+                        const uint64_t c = count_of(i);
+                        if (!c) continue;
+                        std::memcpy(w, a + SMALL_OFF_SLOTS + i * SMALL_SLOTS * P, c * P);
+                        if (flags & SVFM_SORTED) {
+                            if (P == 4) std::sort(reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w) + c);
+                            else std::sort(reinterpret_cast<uint64_t*>(w), reinterpret_cast<uint64_t*>(w) + c);
+                        }
+                        w += c * P;
+                    }
+                }
+                if (alloc_out) *alloc_out = total ? dst : nullptr;
+                return fits ? SVFM_OK : SVFM_ERR_CAPACITY;
+            }
+        }
         PatternBatch pb;
         if ((rc = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return rc;
         if ((rc = unpack_chunk(s, spec, pb))) return rc;
@@ -1082,7 +1258,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
     UploadGroup g;
     if ((rc = begin_group(up.u, cp, pats, offs, fixed_len, flags, g0, g))) break;
     g0 = g.g1;
-    rc = run_workers(ix, g.g0, g.g1, [&](svfm_session* s, uint64_t c) -> int {
+    rc = run_workers(ix, g.g0, g.g1, cp.largest(), [&](svfm_session* s, uint64_t c) -> int {
         if (!s) { publish(c, 0); return SVFM_OK; }
         const uint64_t a = cp.begin(c), b = cp.end(c), m = b - a;
         PatternBatch pb;
@@ -1092,7 +1268,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         if (g_trace) { cudaStreamSynchronize(s->stream); }
         const double t_1 = g_trace ? now_ms() : 0;
         if ((r = unpack_chunk(s, spec, pb))) return r;
-        if ((r = s->out_offs.reserve((m + 1) * sizeof(uint64_t)))) return r;
+        if ((r = s->out_offs.reserve((rsv(s, m) + 1) * sizeof(uint64_t)))) return r;
         void* d_positions = nullptr;
         uint64_t total = 0;
         if ((r = locate_device(s, pb, flags, s->out_offs.ptr, &d_positions, &total))) return r;
@@ -1216,6 +1392,7 @@ void svfm_free(svfm_index* ix) {
         delete u;
     }
     ix->up_pool.clear();
+    if (ix->d_text) cudaFree(ix->d_text);
     if (ix->d_ilv) cudaFree(ix->d_ilv);
     if (ix->d_ext) cudaFree(ix->d_ext);
     if (ix->d_alloc) cudaFree(ix->d_alloc);
@@ -1242,11 +1419,12 @@ int svfm_index_info(const svfm_index* ix, svfm_info* out) {
     return SVFM_OK;
 }
 
-int svfm_index_memory(svfm_index* ix, uint64_t out[4]) {
+int svfm_index_memory(svfm_index* ix, uint64_t out[5]) {
     if (!ix || !out) return SVFM_ERR_BAD_ARG;
     out[0] = ix->blob_len;
     out[1] = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
     out[2] = ix->d_ilv ? ix->L.blocks_len * (uint64_t)ix->ilv_stride : 0;
+    out[4] = ix->d_text ? ix->text_bytes : 0;
     uint64_t scratch = 0;
     std::lock_guard<std::mutex> g(ix->pool_mu);
     for (const svfm_session* s : ix->pool)
@@ -1451,6 +1629,9 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_WORKERS: g_host_workers.store(value); return SVFM_OK;
         case SVFM_TUNE_ILV: g_ilv.store(value); return SVFM_OK;
         case SVFM_TUNE_BUCKET_SORTBACK: g_bucket_sortback.store(value); return SVFM_OK;
+        case SVFM_TUNE_SMALL_MAX: g_small_max.store(value); return SVFM_OK;
+        case SVFM_TUNE_TEXT: g_text.store(value); return SVFM_OK;
+        case SVFM_TUNE_L2_PERSIST: g_l2_persist.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -19,27 +19,29 @@ def fm(request):
     """Every parity test runs with the batch reordering (sweep search for fixed-length batches, locality sort for the
     rest) forced on, forced off (and the kernels reading the blob's occ sections in place instead of the interleaved
     copy), at its default thresholds, and without the extended k-mer table (so that long patterns seed from the blob's
-    own kLTS), and with the reordered batches radix-sorted back into the caller's order instead of the bucketed sort-back:
-    results must not depend on any of it."""
+    own kLTS), and with the reordered batches radix-sorted back into the caller's order instead of the bucketed sort-back;
+    two of the five run without the packed text copy (no text verification): results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
     L = _ffi.lib()
     never = 2**64 - 1
-    sort_min, sweep_min, ext_bits, ilv, bucket = {
-        "reorder_always": (0, 0, 24, 1, 1), "reorder_never": (never, never, 24, 0, 1),
-        "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1, 1),
-        "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1, 1), "radix_sortback": (0, 0, 24, 1, 0)}[request.param]
+    sort_min, sweep_min, ext_bits, ilv, bucket, text = {
+        "reorder_always": (0, 0, 24, 1, 1, 1), "reorder_never": (never, never, 24, 0, 1, 0),
+        "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1, 1, 1),
+        "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1, 1, 1), "radix_sortback": (0, 0, 24, 1, 0, 0)}[request.param]
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, ext_bits) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, text) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, 1)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, 1)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
@@ -246,7 +248,7 @@ def test_load_errors(oracle, fm):
     ix = fm.FmIndex.load(blob, ft)
     assert ix.count(b"ACG") == 2
     mem = ix.memory()  # the blob copy byte for byte; derived structures only when enabled
-    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch"}
+    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch", "text_copy"}
 
 
 def test_medium_random_batch(oracle, fm):
@@ -350,7 +352,7 @@ def test_chunked_host_pipeline(oracle, fm):
             with pytest.raises(fm.EmptyPattern):
                 gpu.locate_batch(var[:5000] + [b""] + var[5000:6000])
     finally:
-        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, _ffi.SVFM_TUNE_AUTO)
 
 
 def test_heavy_patterns_in_fixed_length_batches(oracle, fm):
@@ -499,4 +501,44 @@ def test_packed_patterns_and_u32_offsets(oracle, fm):
                 gpu.pack_patterns(np.full((4, ln), 255, dtype=np.uint8), None, bits)
             gpu.close()
     finally:
-        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, 8 << 20)
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_CHUNK, _ffi.SVFM_TUNE_AUTO)
+
+
+def test_long_patterns_text_verification(oracle, fm):
+    """Long patterns on texts with repeats: the search switches to text verification as soon as a few candidate rows are
+    left (search_kernels.cuh), which must give the reference's answers -- unique hits, absent patterns (mismatch far from the
+    seed), patterns that run into the start of the text, true repeats of the whole pattern (SA-row order!), and reads over
+    repeated regions with one mutated copy."""
+    rng = np.random.default_rng(1505)
+    unit = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=700)]
+    body = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=60_000)]
+    mutated = unit.copy()
+    mutated[350] = ord("A") if mutated[350] != ord("A") else ord("C")
+    text = np.concatenate([unit, body[:20_000], unit, body[20_000:40_000], mutated, body[40_000:], unit[:300]])
+    n = len(text)
+    for (p, nn, v, k, r, syms) in ((32, 2, 64, 3, 2, [b"A", b"C", b"G", b"T"]), (32, 3, 64, 3, 16, [b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"]),
+                                   (64, 3, 128, 2, 5, [b"Aa", b"Cc", b"Gg", b"Tt", b"Nn"]), (64, 4, 32, 4, 1, [b"A", b"C", b"G", b"T"])):
+        ora, gpu, _, _ = _pair(oracle, fm, bytes(text), syms, p, nn, v, k, r)
+        for ln in (33, 64, 150, 400):
+            m = 600
+            starts = rng.integers(0, n - ln, size=m)
+            starts[:40] = rng.integers(0, 700 - min(ln, 600), size=40)             # inside the first copy of the repeat
+            starts[40:60] = 0                                                       # at the very start of the text
+            pats = text[starts[:, None] + np.arange(ln)[None, :]].copy()
+            pats[60:120, 0] = ord("G")                                              # mismatch at the far end (consumed last)
+            pats[120:160, ln // 2] = ord("T")
+            pats[160:170] = text[:ln]
+            pats[160:170, 0] = ord("C") if text[0] != ord("C") else ord("A")        # would need a symbol before the text
+            oc, oo, op_, _ = ora.locate_batch(pats, threads=4)
+            assert int(oc.max()) >= 2 and int(oc.min()) == 0
+            assert np.array_equal(gpu.count_batch(pats).astype(np.uint64), oc), (p, nn, v, ln)
+            offs, pos = gpu.locate_batch(pats)
+            assert np.array_equal(offs, oo) and np.array_equal(pos.astype(np.uint64), op_.astype(np.uint64)), (p, nn, v, ln)
+            var = [bytes(q[: 20 + (i * 7) % (ln - 19)]) for i, q in enumerate(pats[:200])]
+            o2, p2 = gpu.locate_batch(var)
+            for i in (0, 3, 41, 55, 61, 130, 165, 199):
+                assert np.array_equal(p2[int(o2[i]):int(o2[i + 1])].astype(np.uint64), ora.locate(var[i])), (ln, i)
+            for q in (pats[0], pats[45], pats[70], pats[165]):                      # single-pattern calls (small-batch kernel)
+                assert gpu.count(bytes(q)) == ora.count(bytes(q))
+                assert np.array_equal(gpu.locate(bytes(q)).astype(np.uint64), ora.locate(bytes(q)))
+        gpu.close()
