@@ -23,6 +23,7 @@ pub const SVFM_TUNE_BUCKET_SORTBACK: c_int = 6;
 pub const SVFM_TUNE_SMALL_MAX: c_int = 7;
 pub const SVFM_TUNE_TEXT: c_int = 8;
 pub const SVFM_TUNE_L2_PERSIST: c_int = 9;
+pub const SVFM_TUNE_OWN_RADIX: c_int = 10;
 pub const SVFM_TUNE_AUTO: u64 = 0xffff_ffff_ffff_fffe;
 
 #[repr(C)]

@@ -219,9 +219,11 @@ void svfm_host_free(void* p);
  *                      random line per remaining symbol (1 = build, the default; 0 = index only; env SVFM_TEXT).
  * SVFM_TUNE_L2_PERSIST: indexes loaded from now on whose extended k-mer table takes at most this many bytes (default 64 MiB;
  *                      0 = never) mark it persisting in L2 for all their kernels (cudaAccessPolicyWindow).  The default
- *                      2 GiB table is never pinned; this serves deployments that cap SVFM_TUNE_EXT_BITS (env SVFM_L2_PERSIST). */
+ *                      2 GiB table is never pinned; this serves deployments that cap SVFM_TUNE_EXT_BITS (env SVFM_L2_PERSIST).
+ * SVFM_TUNE_OWN_RADIX: the sweep search sorts its items by table index with this library's radix_pass_kernel (1) or with
+ *                      cub::DeviceRadixSort (0, the default: measured 0.84 against 1.36 ms per pass; env SVFM_OWN_RADIX). */
 enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
-       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9 };
+       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9, SVFM_TUNE_OWN_RADIX = 10 };
 #define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */

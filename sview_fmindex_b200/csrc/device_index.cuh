@@ -3,8 +3,19 @@
 // reference's CountArrayView / SuffixArrayView / BwmView, components/*.rs).
 // Citations are relative to the reference's sview-fmindex/src/.
 #pragma once
+#include <cassert>
 #include <cstdint>
 #include <cuda_runtime.h>
+
+// Bounds / protocol assertions inside the kernels, compiled in with -DSVFM_DEBUG_CHECKS (tools/build_variant.sh checks
+// "-DSVFM_DEBUG_CHECKS"; tests/sanitize_case.py runs every kernel of the hot path under that build).  compute-sanitizer
+// is closed on the GPU pool this was developed on, so these device-side asserts are the tool-independent evidence that
+// the look-back protocol, the partition arithmetic and the bucket reservations stay inside their buffers.
+#ifdef SVFM_DEBUG_CHECKS
+#define SVFM_ASSERT(x) assert(x)
+#else
+#define SVFM_ASSERT(x) ((void)0)
+#endif
 
 namespace svfm {
 

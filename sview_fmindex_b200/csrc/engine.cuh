@@ -346,7 +346,8 @@ constexpr int SWEEP_INDEX_BITS = 6;  // PART_INDEX: the last round of `count` gr
 struct SweepPre {
     const uint32_t* prefix;
     const void* pay;   // SweepPay<R>[n]
-    uint32_t* hist;    // [rounds][1 << (bits * steps_per_round)] then [rounds] tile counters
+    uint32_t* hist;    // [rounds][1 << (bits * steps_per_round)] digit histograms of the rounds
+    uint32_t* counters; // [rounds] zeroed tile counters, then 64 zeroed bin cursors (PART_INDEX)
 };
 template <class R>
 int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, uint32_t rounds, SweepPre* out);
@@ -383,7 +384,7 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     const uint32_t* prefix = pre.prefix;
     const Pay* pay = (const Pay*)pre.pay;
     uint32_t* hist = pre.hist;
-    uint32_t* tile_counters = hist + (uint64_t)rounds * nb_max;  // one per round
+    uint32_t* tile_counters = pre.counters;                     // one per round
     uint32_t* bin_cursor = tile_counters + rounds;               // SWEEP_INDEX_BINS counters (PART_INDEX), zeroed with the rest
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);

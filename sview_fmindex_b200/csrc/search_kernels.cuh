@@ -99,6 +99,7 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sy
     sp = (P)(c + ck0 + (P)B::prefix_count(m, r0));
     b1.match_flips(flip, m);
     ep = (P)(c + ck1 + (P)B::prefix_count(m, r1));
+    SVFM_ASSERT(sp <= ep);   // ranks are monotone (with_slice.rs:27: the loop condition relies on it)
 }
 
 // Locality key of a pattern = its trailing symbols packed `bits` per symbol from the top of a u64, the
@@ -184,6 +185,7 @@ __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restri
         }
         pos = (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
         offset += 1;
+        SVFM_ASSERT(s < ix.symbol_count);
     }
 }
 
@@ -294,6 +296,7 @@ __device__ __forceinline__ void search_pattern(const DevIndex<P>& ix, const uint
             t0[c] = 0;
             if (c < rows) {
                 const P pos = locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(sp + c));
+                SVFM_ASSERT((uint64_t)pos < (uint64_t)ix.count_array[ix.symbol_count]);   // a text position
                 if ((uint64_t)pos >= pi) { t0[c] = (uint64_t)pos - pi; alive |= 1u << c; }   // else: it would start before the text
             }
         }
@@ -555,6 +558,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+constexpr uint32_t RADIX_BINS = 256;   // radix_pass_kernel: 8-bit digits
 constexpr int PACK_TILE = 256;    // patterns per tile (= threads per CTA)
 constexpr int PACK_STAGES = 4;    // tiles in flight per CTA
 
@@ -566,7 +570,7 @@ template <class R>
 __global__ void __launch_bounds__(PACK_TILE)
 pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const PatternBatch pb, uint32_t bits, uint32_t m,
                   uint32_t* __restrict__ prefix, SweepPay<R>* __restrict__ pay, uint32_t digit_bits, uint32_t n_rounds,
-                  uint32_t* __restrict__ hist, int* __restrict__ err) {
+                  uint32_t presort_shift, uint32_t presort_passes, uint32_t* __restrict__ hist, int* __restrict__ err) {
     extern __shared__ __align__(128) uint8_t s_tiles[];  // PACK_STAGES x tile_bytes | round histograms
     __shared__ __align__(8) uint64_t s_bar[PACK_STAGES];
     __shared__ uint16_t s_lut[256];                       // byte -> symbol index | rank << 8
@@ -574,10 +578,14 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     const uint32_t S = syms.symbol_count;
     const uint32_t tile_bytes = PACK_TILE * len;
     const uint32_t stage_stride = (tile_bytes + 127u) & ~127u;
-    // digit histograms of the partition rounds (sweep_round_kernel): round r sorts on bits [r*digit_bits, +digit_bits) of rest
+    // digit histograms of the partition rounds (sweep_round_kernel): round r sorts on bits [r*digit_bits, +digit_bits) of rest;
+    // behind them the 256-bin histograms of the presort passes (radix_pass_kernel): pass q sorts on bits
+    // [presort_shift + 8q, +8) of the table index
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_tiles + (size_t)PACK_STAGES * stage_stride);
     const uint32_t nb = 1u << digit_bits;
-    for (uint32_t i = threadIdx.x; i < n_rounds * nb; i += blockDim.x) s_hist[i] = 0;
+    const uint32_t n_hist = n_rounds * nb + presort_passes * RADIX_BINS;
+    uint32_t* s_phist = s_hist + n_rounds * nb;
+    for (uint32_t i = threadIdx.x; i < n_hist; i += blockDim.x) s_hist[i] = 0;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t sidx = (table && !pb.preencoded) ? table[i] : (uint32_t)i;
         const uint32_t bad = sidx >= S ? 0x8000u : 0u;     // PassThrough byte >= S
@@ -634,8 +642,10 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
         }
         if (flags & 0x8000u) errbits |= ERRBIT_BAD_SYMBOL;
         // 0x4000: a symbol that never occurs in the text -- count 0, wherever it sits in the pattern
-        prefix[i] = (flags & 0x4000u) ? 0xffffffffu : e;
+        const uint32_t pfx = (flags & 0x4000u) ? 0xffffffffu : e;
+        prefix[i] = pfx;
         for (uint32_t r = 0; r < n_rounds; r++) atomicAdd(&s_hist[r * nb + (uint32_t)((rest >> (r * digit_bits)) & (R)(nb - 1))], 1u);
+        for (uint32_t q = 0; q < presort_passes; q++) atomicAdd(&s_phist[q * RADIX_BINS + ((pfx >> (presort_shift + 8u * q)) & (RADIX_BINS - 1u))], 1u);
         SweepPay<R> o;
         o.rest = rest;
         o.idx = (uint32_t)i;
@@ -672,9 +682,150 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
         if (i0 + threadIdx.x < pb.n) pack_one(stage + (uint64_t)threadIdx.x * len, i0 + threadIdx.x);
         __syncthreads();
     }
-    for (uint32_t i = threadIdx.x; i < n_rounds * nb; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < n_hist; i += blockDim.x)
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
     if (errbits) atomicOr(err, errbits);
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr uint32_t DESC_AGG = 1u << 30, DESC_PREFIX = 2u << 30, DESC_MASK = (1u << 30) - 1;
+
+// ---- one stable LSD radix pass over the packed items (table index -> payload), 8-bit digit ---------------------------------
+// The sort of the sweep items by table index runs on this kernel (round 1 used cub::DeviceRadixSort): the same building
+// blocks as the partition half of sweep_round_kernel -- tiles handed out by an atomic counter, stable rank inside the digit
+// by warp match + per-warp counters, exclusive prefix over all earlier tiles by decoupled look-back (one descriptor word per
+// tile and digit; one thread per digit walks back), shared-memory exchange so that every digit's run leaves with coalesced
+// stores.  The batch histogram of the digit comes from pack_sweep_kernel.  Stable, so that two passes sort 16 bits.
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_ITEMS = 8;
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;
+constexpr int RADIX_WARPS = RADIX_THREADS / 32;
+template <class R>
+__global__ void __launch_bounds__(RADIX_THREADS)
+radix_pass_kernel(const uint32_t* __restrict__ key_in, const SweepPay<R>* __restrict__ pay_in, uint32_t* __restrict__ key_out,
+                  SweepPay<R>* __restrict__ pay_out, uint64_t n, uint32_t shift, const uint32_t* __restrict__ hist,
+                  uint32_t* desc, uint32_t* tile_counter) {
+    using Pay = SweepPay<R>;
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    Pay* s_pay = reinterpret_cast<Pay*>(s_dyn);                                  // RADIX_TILE
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_pay + RADIX_TILE);          // RADIX_TILE
+    uint32_t* s_whist = s_key + RADIX_TILE;                                       // RADIX_WARPS x RADIX_BINS
+    __shared__ uint32_t s_binstart[RADIX_BINS], s_tilebin[RADIX_BINS], s_gbase[RADIX_BINS], s_scan[RADIX_WARPS], s_tile;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    {   // global start of every digit: exclusive scan of the batch histogram (one bin per thread)
+        const uint32_t v = hist[threadIdx.x];
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(full, incl, d);
+            if ((int)lane >= d) incl += o;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t off = 0;
+        for (uint32_t w = 0; w < warp; w++) off += s_scan[w];
+        s_binstart[threadIdx.x] = off + incl - v;
+    }
+    __syncthreads();
+    const uint64_t n_tiles = (n + RADIX_TILE - 1) / RADIX_TILE;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        __syncthreads();
+        if (tile >= n_tiles) break;
+        const uint64_t base = tile * RADIX_TILE + (uint64_t)warp * (32 * RADIX_ITEMS) + lane;
+        uint32_t key[RADIX_ITEMS], rank[RADIX_ITEMS];
+        Pay pay[RADIX_ITEMS];
+#pragma unroll
+        for (int k = 0; k < RADIX_ITEMS; k++) {
+            const uint64_t w = base + (uint64_t)k * 32;
+            key[k] = 0;
+            if (w < n) { key[k] = key_in[w]; pay[k] = pay_in[w]; }
+        }
+        for (uint32_t i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS; i += RADIX_THREADS) s_whist[i] = 0;
+        __syncthreads();
+        uint32_t* my_hist = s_whist + warp * RADIX_BINS;
+#pragma unroll
+        for (int k = 0; k < RADIX_ITEMS; k++) {
+            const bool valid = base + (uint64_t)k * 32 < n;
+            const uint32_t dig = valid ? ((key[k] >> shift) & (RADIX_BINS - 1u)) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(full, dig);
+            const int leader = __ffs(peers) - 1;
+            uint32_t before = 0;
+            if ((int)lane == leader && valid) {
+                before = my_hist[dig];
+                my_hist[dig] = before + __popc(peers);
+            }
+            before = __shfl_sync(full, before, leader);
+            rank[k] = before + __popc(peers & ((1u << lane) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // one digit per thread: offsets of the warps inside the tile, tile total, look-back, position of the digit's run
+            const uint32_t b = threadIdx.x;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX_WARPS; w++) {
+                const uint32_t t = s_whist[w * RADIX_BINS + b];
+                s_whist[w * RADIX_BINS + b] = acc;
+                acc += t;
+            }
+            st_volatile_u32(desc + tile * RADIX_BINS + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+            uint32_t excl = 0;
+            if (tile > 0) {
+                for (uint64_t t = tile - 1;; t--) {
+                    uint32_t v;
+                    do { v = ld_volatile_u32(desc + t * RADIX_BINS + b); } while ((v >> 30) == 0);
+                    excl += v & DESC_MASK;
+                    if ((v >> 30) == 2u || t == 0) break;
+                }
+                st_volatile_u32(desc + tile * RADIX_BINS + b, DESC_PREFIX | (excl + acc));
+            }
+            // exclusive scan of the tile totals over the digits: where the digit's run starts inside the exchange buffer
+            uint32_t incl = acc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(full, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            uint32_t run = incl - acc;
+            for (uint32_t w = 0; w < warp; w++) run += s_scan[w];
+            s_tilebin[b] = run;
+            s_gbase[b] = s_binstart[b] + excl - run;   // global position = gbase[digit] + slot in the buffer (mod 2^32: n < 2^30)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RADIX_ITEMS; k++) {
+            if (base + (uint64_t)k * 32 < n) {
+                const uint32_t dig = (key[k] >> shift) & (RADIX_BINS - 1u);
+                const uint32_t slot = s_tilebin[dig] + my_hist[dig] + rank[k];
+                SVFM_ASSERT(slot < (uint32_t)RADIX_TILE);
+                s_key[slot] = key[k];
+                s_pay[slot] = pay[k];
+            }
+        }
+        __syncthreads();
+        const uint32_t tile_n = (uint32_t)(n - tile * RADIX_TILE < (uint64_t)RADIX_TILE ? n - tile * RADIX_TILE : (uint64_t)RADIX_TILE);
+        for (uint32_t j = threadIdx.x; j < tile_n; j += RADIX_THREADS) {
+            const uint32_t kk = s_key[j];
+            const uint32_t g = s_gbase[(kk >> shift) & (RADIX_BINS - 1u)] + j;
+            SVFM_ASSERT((uint64_t)g < n);
+            key_out[g] = kk;
+            pay_out[g] = s_pay[j];
+        }
+        __syncthreads();
+    }
 }
 
 // State of one pattern between rounds.  16 bytes for u32 positions and <= 32 bits of remaining symbols (one
@@ -706,7 +857,6 @@ constexpr int ROUND_WARPS = ROUND_THREADS / 32;
 constexpr int ROUND_MAX_BINS = 512;
 constexpr int ROUND_LB = SVFM_ROUND_LB;                     // look-back: descriptors polled per thread and step (0: one
                                                             // thread per digit walks back alone -- measured faster, see below)
-constexpr uint32_t DESC_AGG = 1u << 30, DESC_PREFIX = 2u << 30, DESC_MASK = (1u << 30) - 1;
 enum : int { PART_NONE = 0, PART_SYMBOLS = 1, PART_INDEX = 2 };
 
 template <class P, class R>
@@ -733,14 +883,6 @@ struct SweepRoundIO {
     SbOut sb;                  // last round of `locate`: bucket sizes of the bucketed sort-back
 };
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // One round of the sweep search, fused with the radix partition that follows it:
 //   load a tile of items (FIRST: seed them from the extended table) -> `steps` backward steps each
@@ -965,6 +1107,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                         uint32_t v;
                         do { v = ld_volatile_u32(io.desc + t * nbins + b); } while ((v >> 30) == 0);
                         excl += v & DESC_MASK;
+                        SVFM_ASSERT((uint64_t)excl <= n);
                         if ((v >> 30) == 2u || t == 0) break;
                     }
                     st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + acc));
@@ -1007,6 +1150,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         for (int k = 0; k < ROUND_ITEMS; k++) {
             if (dig[k] != 0xffffffffu) {
                 const uint32_t slot = s_tilebin[dig[k]] + my_hist[dig[k]] + rank[k];
+                SVFM_ASSERT(dig[k] < nbins && slot < (uint32_t)ROUND_TILE);
                 Item v; v.sp = sp[k]; v.cnt = cnt[k]; v.rest = rest[k]; v.idx = idx[k];
                 s_items[slot] = v;
             }
@@ -1019,6 +1163,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
             if constexpr (PART == PART_INDEX) d = v.idx >> io.idx_shift;
             else d = (uint32_t)((v.rest >> shift) & digit_mask);
             const uint64_t g = s_gbase[d] + j;
+            SVFM_ASSERT(d < nbins && g < n);   // every digit's run stays inside the batch: histogram + look-back / reservation agree
             if (io.items_out) io.items_out[g] = v;
             if (io.sp_out) io.sp_out[g] = v.sp;
             if (io.cnt_out) io.cnt_out[g] = v.cnt;
@@ -1377,6 +1522,7 @@ sb_place_kernel(const SbRec<P>* __restrict__ recs, const uint64_t* __restrict__ 
         const SbRec<P> r = rb[p];
         const uint32_t k = sb_pad(r.idx & (SB_BUCKET - 1));
         const uint32_t slot = s_off[k] + (p - s_first[k]);
+        SVFM_ASSERT((r.idx >> SB_SHIFT) == b && p >= s_first[k] && slot < m);   // the record is in its own bucket, inside its pattern's run
         if (staged) s_pos[slot] = r.pos;
         else out[slot] = r.pos;
     }

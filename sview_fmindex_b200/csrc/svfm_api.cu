@@ -245,6 +245,10 @@ static std::atomic<uint64_t> g_bucket_sortback{[] {  // 1: bucketed sort-back (s
     const char* e = std::getenv("SVFM_BUCKET_SORTBACK");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
+static std::atomic<uint64_t> g_own_radix{[] {  // sweep presort: 1 = radix_pass_kernel, 0 = cub::DeviceRadixSort
+    const char* e = std::getenv("SVFM_OWN_RADIX");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)0;
+}()};
 static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once more after the last round
     const char* e = std::getenv("SVFM_SWEEP_FINAL_SORT");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
@@ -392,7 +396,8 @@ static int run_sortback_records(svfm_session* s, uint64_t n, uint64_t total, boo
     return SVFM_OK;
 }
 
-// Front of the sweep search, independent of the index type: pack_sweep_kernel + radix sort by table index.
+// Front of the sweep search, independent of the index type: pack_sweep_kernel + radix sort by table index
+// (radix_pass_kernel, search_kernels.cuh).
 template <class R>
 int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, uint32_t rounds, SweepPre* out) {
     const svfm_index* ix = s->ix;
@@ -400,34 +405,53 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     const uint64_t n = pb.n;
     const uint32_t len = pb.fixed_len, bits = plan.bits;
     const uint32_t digit_bits = bits * plan.steps_per_round, nb_max = 1u << digit_bits;
-    int rc;
-    const uint64_t rn = rsv(s, n);
-    if ((rc = s->keys0.reserve(rn * 4)) || (rc = s->keys1.reserve(rn * 4)) || (rc = s->pay0.reserve(rn * sizeof(Pay))) ||
-        (rc = s->pay1.reserve(rn * sizeof(Pay))) || (rc = s->sweep_hist.reserve(((uint64_t)rounds * nb_max + rounds + 64) * 4)))
-        return rc;
-    cub::DoubleBuffer<uint32_t> prefix((uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr);
-    cub::DoubleBuffer<Pay> pay((Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr);
-    uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
-    size_t t1 = 0;
     // Only the top 16 bits of the table index are sorted (two radix passes).  Items that differ in the lower bits only sit
     // within 1/65536 of the SA (a 2^28-entry DNA table on 1 Gbp: 4096 entries, ~240 occ blocks = 10 KB of index data, which
     // the CTAs working on that stretch share through L1/L2), and correctness never depends on the order.  Measured on B200,
     // 10^8 20-mers: 28 bits (4 passes) and 24 bits (3 passes) give the same round times; 16 bits make the first round
     // 0.6 ms slower and the sort 0.85 ms shorter (14.65 against 14.87 ms per batch); SVFM_PRESORT_BITS overrides.
     static const int sort_bits = [] { const char* e = std::getenv("SVFM_PRESORT_BITS"); return e ? atoi(e) : 16; }();
-    const int sort_begin = plan.prefix_bits > sort_bits ? plan.prefix_bits - sort_bits : 0;
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, prefix, pay, (int64_t)n, sort_begin, plan.prefix_bits, s->stream));
-    if ((rc = s->cub_temp.reserve(t1))) return rc;
+    const uint32_t sort_begin = plan.prefix_bits > sort_bits ? (uint32_t)(plan.prefix_bits - sort_bits) : 0u;
+    // Who sorts: cub::DeviceRadixSort (onesweep) by default, this repo's radix_pass_kernel with SVFM_OWN_RADIX=1.  Measured
+    // on B200, 10^8 items of 12 bytes, 8-bit digit: 0.84 ms per pass (cub) against 1.36 ms (radix_pass_kernel: a third of its
+    // warp samples wait in the look-back, 10.6 polls per tile and digit; profiles/r2_radix_pass_ncu.txt) -- the library
+    // kernel stays on the path until the own one is at least as fast.
+    const bool own_radix = g_own_radix.load() != 0;
+    const uint32_t passes = own_radix ? ((uint32_t)plan.prefix_bits - sort_begin + 7) / 8 : 0u;
+    // histogram words: [rounds x nb_max] round digits | [passes x 256] presort digits | [rounds] round tile counters |
+    // [64] PART_INDEX bin cursors | [passes] presort tile counters
+    const uint64_t off_phist = (uint64_t)rounds * nb_max;
+    const uint64_t off_counters = off_phist + (uint64_t)passes * RADIX_BINS;
+    const uint64_t off_ptile = off_counters + rounds + 64;
+    const uint64_t hist_words = off_ptile + passes + 8;
+    const uint64_t rn = rsv(s, n);
+    const uint64_t radix_tiles = (rn + RADIX_TILE - 1) / RADIX_TILE;
+    int rc;
+    if ((rc = s->keys0.reserve(rn * 4)) || (rc = s->keys1.reserve(rn * 4)) || (rc = s->pay0.reserve(rn * sizeof(Pay))) ||
+        (rc = s->pay1.reserve(rn * sizeof(Pay))) || (rc = s->sweep_hist.reserve(hist_words * 4)) ||
+        (rc = s->sweep_desc.reserve(radix_tiles * RADIX_BINS * 4)))
+        return rc;
+    uint32_t* key[2] = {(uint32_t*)s->keys0.ptr, (uint32_t*)s->keys1.ptr};
+    Pay* pay[2] = {(Pay*)s->pay0.ptr, (Pay*)s->pay1.ptr};
+    uint32_t* hist = (uint32_t*)s->sweep_hist.ptr;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
-    PhaseTimer pt(s, SVFM_PHASE_PRESORT, 2 + (plan.prefix_bits - sort_begin + 7) / 8);
-    SVFM_CUDA(cudaMemsetAsync(hist, 0, ((uint64_t)rounds * nb_max + rounds + 64) * 4, s->stream));
+    cub::DoubleBuffer<uint32_t> ckey(key[0], key[1]);
+    cub::DoubleBuffer<Pay> cpay(pay[0], pay[1]);
+    size_t t1 = 0;
+    if (!own_radix) {
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, ckey, cpay, (int64_t)n, (int)sort_begin, plan.prefix_bits, s->stream));
+        if ((rc = s->cub_temp.reserve(t1))) return rc;
+    }
+    PhaseTimer pt(s, SVFM_PHASE_PRESORT, own_radix ? 1 + passes : 2 + (plan.prefix_bits - sort_begin + 7) / 8);
+    SVFM_CUDA(cudaMemsetAsync(hist, 0, hist_words * 4, s->stream));
     const uint8_t* table = ix->type.encoder ? ix->d_blob + ix->L.off_encoder : nullptr;
     DevSyms syms;
     syms.symbol_count = ix->L.symbol_count;
     syms.s_eff = ix->symbols_present;
     std::memcpy(syms.sym_rank, ix->sym_rank, 64);
-    const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) + (size_t)rounds * nb_max * 4;
+    const size_t smem = (size_t)PACK_STAGES * (((size_t)PACK_TILE * len + 127) & ~(size_t)127) +
+                        ((size_t)rounds * nb_max + (size_t)passes * RADIX_BINS) * 4;
     // always the same value (concurrent sessions pack batches of different pattern lengths; the attribute is per function)
     SVFM_CUDA(cudaFuncSetAttribute(pack_sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYNAMIC_SMEM));
     if (smem > (size_t)MAX_DYNAMIC_SMEM) return SVFM_ERR_TOO_LARGE;
@@ -435,13 +459,37 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pack_sweep_kernel<R>, PACK_TILE, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     uint64_t grid = (n + PACK_TILE - 1) / PACK_TILE;
     if (grid > (uint64_t)sms * per_sm) grid = (uint64_t)sms * per_sm;
-    pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, plan.m, prefix.Current(), pay.Current(),
-                                                                        digit_bits, rounds, hist, s->d_err);
+    pack_sweep_kernel<R><<<(unsigned)grid, PACK_TILE, smem, s->stream>>>(table, syms, pb, bits, plan.m, key[0], pay[0], digit_bits, rounds,
+                                                                        sort_begin, passes, hist, s->d_err);
     SVFM_CUDA(cudaGetLastError());
-    SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, prefix, pay, (int64_t)n, sort_begin, plan.prefix_bits, s->stream));
-    out->prefix = prefix.Current();
-    out->pay = pay.Current();
+    if (!own_radix) {
+        SVFM_CUDA(cub::DeviceRadixSort::SortPairs(s->cub_temp.ptr, t1, ckey, cpay, (int64_t)n, (int)sort_begin, plan.prefix_bits, s->stream));
+        out->prefix = ckey.Current();
+        out->pay = cpay.Current();
+        out->hist = hist;
+        out->counters = hist + off_counters;
+        return SVFM_OK;
+    }
+    // stable LSD passes, 8 bits each
+    const size_t rsmem = (size_t)RADIX_TILE * (sizeof(Pay) + 4) + (size_t)RADIX_WARPS * RADIX_BINS * 4;
+    SVFM_CUDA(cudaFuncSetAttribute(radix_pass_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYNAMIC_SMEM));
+    int rper = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, radix_pass_kernel<R>, RADIX_THREADS, rsmem) != cudaSuccess || rper < 1) rper = 1;
+    const uint64_t n_tiles = (n + RADIX_TILE - 1) / RADIX_TILE;
+    const uint64_t rgrid = n_tiles < (uint64_t)sms * rper ? n_tiles : (uint64_t)sms * rper;
+    int cur = 0;
+    for (uint32_t q = 0; q < passes; q++) {
+        SVFM_CUDA(cudaMemsetAsync(s->sweep_desc.ptr, 0, n_tiles * RADIX_BINS * 4, s->stream));
+        radix_pass_kernel<R><<<(unsigned)rgrid, RADIX_THREADS, rsmem, s->stream>>>(key[cur], pay[cur], key[cur ^ 1], pay[cur ^ 1], n,
+                                                                                 sort_begin + 8 * q, hist + off_phist + (uint64_t)q * RADIX_BINS,
+                                                                                 (uint32_t*)s->sweep_desc.ptr, hist + off_ptile + q);
+        SVFM_CUDA(cudaGetLastError());
+        cur ^= 1;
+    }
+    out->prefix = key[cur];
+    out->pay = pay[cur];
     out->hist = hist;
+    out->counters = hist + off_counters;
     return SVFM_OK;
 }
 template int run_sweep_presort<uint32_t>(svfm_session*, const PatternBatch&, const SortPlan&, uint32_t, SweepPre*);
@@ -1632,6 +1680,7 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_SMALL_MAX: g_small_max.store(value); return SVFM_OK;
         case SVFM_TUNE_TEXT: g_text.store(value); return SVFM_OK;
         case SVFM_TUNE_L2_PERSIST: g_l2_persist.store(value); return SVFM_OK;
+        case SVFM_TUNE_OWN_RADIX: g_own_radix.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;
     }
 }

@@ -20,7 +20,8 @@ def fm(request):
     rest) forced on, forced off (and the kernels reading the blob's occ sections in place instead of the interleaved
     copy), at its default thresholds, and without the extended k-mer table (so that long patterns seed from the blob's
     own kLTS), and with the reordered batches radix-sorted back into the caller's order instead of the bucketed sort-back;
-    two of the five run without the packed text copy (no text verification): results must not depend on any of it."""
+    two of the five run without the packed text copy (no text verification), one sorts the sweep items with this library's
+    own radix pass instead of cub: results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
     L = _ffi.lib()
@@ -35,6 +36,7 @@ def fm(request):
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, text) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 1 if request.param == "radix_sortback" else 0) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, _ffi.SVFM_TUNE_AUTO)
@@ -42,6 +44,7 @@ def fm(request):
     L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, 1)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 0)
 
 
 def _pair(po, fm, text, symbols, p, n, v, k, r, passthrough=False, with_wildcard=False):
