@@ -602,7 +602,6 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     const bool tma_ok = (reinterpret_cast<uintptr_t>(pb.pats) & 15u) == 0;  // tile_bytes = 256 * len is a multiple of 16
     int errbits = 0;
 
-    const bool words_ok = (len & 3u) == 0;  // a pattern then starts on a 4-byte boundary of the staged tile
     // The kernel is issue-bound (ncu, round 1: 86 % of the issue slots busy), so the common case -- forward patterns whose
     // length is a multiple of four -- takes a lean loop: one word load per four symbols, one table lookup and one
     // multiply-add per symbol (the stored bytes run from the symbol consumed last to the one consumed first, so both the
@@ -610,20 +609,24 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     auto pack_one = [&](const uint8_t* p, uint64_t i) {
         uint32_t e = 0, flags = 0;
         R rest = 0;
-        if (words_ok && !pb.reversed) {
-            const uint32_t* pw = reinterpret_cast<const uint32_t*>(p);
-            const uint32_t n_rest = len - m;  // stored bytes [0, n_rest) are the remaining symbols, [n_rest, len) the table index
+        if (!pb.reversed) {
+            // stored bytes [0, n_rest) are the remaining symbols (Horner: the byte consumed first, right before the table's
+            // m symbols, ends up lowest), [n_rest, len) the table index.  Two plain loops over the staged bytes: one byte load,
+            // one table lookup and one shift-or / multiply-add per symbol (the kernel is issue-bound; the earlier single loop
+            // with a per-symbol branch on the byte's role cost 20 instructions per symbol).
+            const uint32_t n_rest = len - m;
             uint32_t f = 0;
-            for (uint32_t w = 0; w < (len >> 2); w++) {
-                const uint32_t word = pw[w];
-#pragma unroll
-                for (int b = 0; b < 4; b++, f++) {
-                    const uint32_t v = s_lut[(word >> (8 * b)) & 0xffu];
-                    flags |= v;
-                    const uint32_t r = (v >> 8) & 0x3fu;
-                    if (f < n_rest) rest = (R)((rest << bits) | (R)r);
-                    else e = e * syms.s_eff + r;
-                }
+#pragma unroll 4
+            for (; f < n_rest; f++) {
+                const uint32_t v = s_lut[p[f]];
+                flags |= v;
+                rest = (R)((rest << bits) | (R)((v >> 8) & 0x3fu));
+            }
+#pragma unroll 4
+            for (; f < len; f++) {
+                const uint32_t v = s_lut[p[f]];
+                flags |= v;
+                e = e * syms.s_eff + ((v >> 8) & 0x3fu);
             }
         } else {
             uint32_t mult = 1;
