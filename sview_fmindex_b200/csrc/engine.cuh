@@ -362,7 +362,7 @@ extern template int run_sweep_presort<uint64_t>(svfm_session*, const PatternBatc
 // slots of the bucketed sort-back.
 template <class P, int NPL, int VBITS, class R>
 static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,
-                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {
+                              void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb, uint8_t* d_resolved) {
     const svfm_index* ix = s->ix;
     const DevIndex<P> dix = make_dev_index<P>(ix);
     const uint64_t n = pb.n;
@@ -390,10 +390,29 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
     uint32_t* idx_work = (uint32_t*)s->vals0.ptr;
     int cur = 0;  // items[cur] holds the current state from round 1 on
+    // locate mode with a text copy: the last round can resolve instead of stepping + partitioning (sweep_resolve_kernel).
+    // OFF by default -- measured on B200, 10^8 20-mers: resolve 5.96 ms + locate 2.94 ms against last round 2.85 ms + locate
+    // 4.88 ms: the text check adds one random sector per item (1.8 ms at the random-access rate), more than the skipped
+    // backward steps and partition cost once the batch is SA-ordered.  SVFM_SWEEP_RESOLVE=1 turns it on.
+    static const bool resolve_env = [] { const char* e = std::getenv("SVFM_SWEEP_RESOLVE"); return e ? atoi(e) != 0 : false; }();
+    const bool resolve_last = resolve_env && final_mode == PART_SYMBOLS && rounds >= 2 && dix.text != nullptr && d_resolved != nullptr;
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t first = r * T;
         const uint32_t steps = remaining - first < T ? remaining - first : T;
         const bool last = r + 1 == rounds;
+        if (last && resolve_last) {
+            PhaseTimer pt(s, SVFM_PHASE_SEARCH, 1);
+            auto launch = [&](auto kernel) -> int {
+                const int grid = resident_grid(kernel, n, 256, ix->device);
+                kernel<<<grid, 256, 0, s->stream>>>(dix, items[cur], n, bits, bits * first, steps, (P*)d_sp_work, (P*)d_cnt_work, idx_work,
+                                                    d_resolved, s->d_counters, sb);
+                SVFM_CUDA(cudaGetLastError());
+                return SVFM_OK;
+            };
+            rc = dix.ilv ? launch(sweep_resolve_kernel<P, NPL, VBITS, R, true>) : launch(sweep_resolve_kernel<P, NPL, VBITS, R, false>);
+            if (rc) return rc;
+            break;
+        }
         int part = PART_SYMBOLS;
         if (last) part = final_mode == PART_INDEX ? PART_INDEX : (final_mode == PART_SYMBOLS && steps > 0 ? PART_SYMBOLS : PART_NONE);
         // the last partition digit may be narrower than digit_bits: the histogram was taken on digit_bits bits, whose
@@ -460,9 +479,9 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
 
 template <class P, int NPL, int VBITS>
 static int run_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode, void* d_sp_work,
-                            void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {
-    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb);
-    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb);
+                            void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb, uint8_t* d_resolved) {
+    if (plan.rest64) return run_search_sweep_r<P, NPL, VBITS, uint64_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb, d_resolved);
+    return run_search_sweep_r<P, NPL, VBITS, uint32_t>(s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb, d_resolved);
 }
 
 template <class P>
@@ -563,7 +582,7 @@ struct TypeOps {
     int (*build_ext)(uint32_t planes, svfm_index* ix, uint64_t ext_bits);
     int (*build_text)(uint32_t planes, svfm_index* ix);
     int (*search_sweep)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,
-                        void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb);
+                        void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb, uint8_t* d_resolved);
     int (*small)(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SmallOut& out);
     int (*locate)(uint32_t planes, svfm_session* s, uint64_t n, const uint32_t* idx, const void* d_sp_work, const void* d_cnt_work,
                   const uint64_t* d_offs, uint64_t total, uint64_t heavy_seen, void* d_positions, uint32_t* d_rec_key,
@@ -593,8 +612,9 @@ struct TypeOps {
         SVFM_PLANES_SWITCH(P, VB, run_build_text, ix)                                                                               \
     }                                                                                                                               \
     static int NAME##_search_sweep(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode,  \
-                                   void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb) {      \
-        SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb)               \
+                                   void* d_sp_work, void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb,        \
+                                   uint8_t* d_resolved) {                                                                           \
+        SVFM_PLANES_SWITCH(P, VB, run_search_sweep, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb, d_resolved)   \
     }                                                                                                                               \
     static int NAME##_small(uint32_t planes, svfm_session* s, const PatternBatch& pb, const SmallOut& out) {                        \
         SVFM_PLANES_SWITCH(P, VB, run_small, s, pb, out)                                                                            \

@@ -1182,6 +1182,67 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     }
 }
 
+// ---- last round of the sweep search in `locate` mode: resolve instead of step (opt-in, SVFM_SWEEP_RESOLVE=1) ------------
+// (Measured slower than the plain last round on SA-ordered batches -- see engine.cuh -- and therefore off by default.)
+// After the first rounds almost every item of a typical batch is down to ONE SA row (20-mers on 1 Gbp: 94 % after 17
+// symbols).  Locating that row costs the same LF walk + SA read that `locate` would pay after the last round anyway, and
+// with the row's text position in hand the symbols that are still unread can be checked against the packed text copy (one
+// more sector) instead of being walked through the index and partitioned once more: such an item is RESOLVED here (count 0
+// or 1, sp = the text position; see "text verification").  Items with more than one row take their remaining backward steps
+// on the spot (with_slice.rs:27-31) and are located row by row later, as before.  The items arrive sorted by SA position
+// (they were partitioned by the previous round), so the LF walks and SA reads of this kernel stream like those of
+// locate_warp_kernel did; outputs stay in that order.
+template <class P, int NPL, int VBITS, class R, bool ILV>
+__global__ void __launch_bounds__(256)
+sweep_resolve_kernel(const DevIndex<P> ix, const SweepItem<P, R>* __restrict__ items, uint64_t n, uint32_t bits, uint32_t shift,
+                     uint32_t steps, P* __restrict__ sp_out, P* __restrict__ cnt_out, uint32_t* __restrict__ idx_out,
+                     uint8_t* __restrict__ resolved_out, unsigned long long* heavy_seen, SbOut sb) {
+    __shared__ P s_count[65];
+    __shared__ uint8_t s_present[64];
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_present[i] = ix.present[i];
+    __syncthreads();
+    const R sym_mask = (R)((1ull << bits) - 1);
+    unsigned long long rows = 0;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += (uint64_t)gridDim.x * blockDim.x) {
+        const SweepItem<P, R> it = items[w];
+        P sp = it.sp, cnt = it.cnt;
+        const R left = (R)(it.rest >> shift);   // rank of the t-th symbol still to be consumed: (left >> bits*t) & mask
+        bool resolved = false;
+        if (cnt == 1) {
+            const P pos = locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp);
+            bool same = (uint64_t)pos >= steps;   // else the pattern would start before the text does
+            for (uint32_t t = 0; t < steps && same; t++)
+                same = text_symbol(ix.text, ix.text_bits, (uint64_t)pos - 1 - t) == (uint32_t)((left >> (bits * t)) & sym_mask);
+            sp = same ? (P)(pos - (P)steps) : (P)0;
+            cnt = same ? 1 : 0;
+            resolved = same;
+        } else if (cnt != 0) {
+            P ep = (P)(sp + cnt);
+            R l2 = left;
+            for (uint32_t t = 0; t < steps && sp < ep; t++, l2 >>= bits) {
+                const uint32_t sy = s_present[(uint32_t)(l2 & sym_mask)];
+                backward_step<P, NPL, VBITS>(ix, sy, s_count[sy], sp, ep);
+            }
+            cnt = (P)(ep - sp);
+        }
+        sp_out[w] = sp;
+        cnt_out[w] = cnt;
+        idx_out[w] = it.idx;
+        resolved_out[w] = resolved ? 1 : 0;
+        if (heavy_seen && (uint64_t)cnt > HEAVY_ROWS) atomicAdd(heavy_seen, 1ull);
+        if (sb.hist && cnt != 0) {
+            atomicAdd(sb.hist + (it.idx >> SB_SHIFT), (uint32_t)cnt);
+            rows += (unsigned long long)cnt;
+        }
+    }
+    if (sb.hist) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
+        if ((threadIdx.x & 31) == 0 && rows) atomicAdd(sb.total, rows);
+    }
+}
+
 // ---- small batches (a few thousand patterns at most; every single-pattern call) -------------------------------------
 // ONE launch does search and locate: a thread takes one pattern, runs the backward search and walks up to `slots_per` of
 // its SA rows into a fixed slot array; the host turns counts + slots into the CSR result (or, when some pattern has more

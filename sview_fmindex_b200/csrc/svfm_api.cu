@@ -514,9 +514,9 @@ static int dispatch_search(svfm_session* s, const PatternBatch& pb, const uint64
     return ops ? ops->search(s->ix->type.planes, s, pb, keys, idx, bits, d_sp_work, d_cnt_work, sb, d_resolved) : SVFM_ERR_BAD_TYPE;
 }
 static int dispatch_search_sweep(svfm_session* s, const PatternBatch& pb, const SortPlan& plan, int final_mode, void* d_sp_work,
-                                 void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb = SbOut{}) {
+                                 void* d_cnt_work, const uint32_t** idx_out, const SbOut& sb = SbOut{}, uint8_t* d_resolved = nullptr) {
     const TypeOps* ops = type_ops(s->ix->type);
-    return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb)
+    return ops ? ops->search_sweep(s->ix->type.planes, s, pb, plan, final_mode, d_sp_work, d_cnt_work, idx_out, sb, d_resolved)
                : SVFM_ERR_BAD_TYPE;
 }
 // Interleaved occ copy: { block q | checkpoint row q } per aligned slot.  Derived from the blob, bytes only.
@@ -692,8 +692,16 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         SVFM_CUDA(cudaMemsetAsync(sb.hist, 0, nb * 4, s->stream));
     }
     if (plan.sweep) {
+        uint8_t* res = nullptr;
+        if (s->ix->d_text) {
+            if ((rc = s->resolved.reserve(rn))) return rc;
+            res = (uint8_t*)s->resolved.ptr;
+            // all zero unless the last round resolves (then every flag is written): locate reads the array either way
+            SVFM_CUDA(cudaMemsetAsync(res, 0, pb.n, s->stream));
+            d_resolved = res;
+        }
         if ((rc = dispatch_search_sweep(s, pb, plan, g_sweep_final_sort.load() != 0 ? PART_SYMBOLS : PART_NONE, s->sp.ptr, s->cnt.ptr,
-                                        &idx, sb)))
+                                        &idx, sb, res)))
             return rc;
     } else {
         if (plan.sorted && (rc = run_presort(s, pb, plan, &keys, &idx))) return rc;
