@@ -176,8 +176,23 @@ __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restri
         if constexpr (ILV) {
             const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
             b.load_aligned(e);
-            s = b.symidx_of(rem);
-            ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
+            if (sizeof(P) == 4 && ix.symbol_count <= 8 && (ix.ilv_ck_off & 7u) == 0) {   // (row end stays inside the slot: DESIGN.md)
+                // Which checkpoint word is needed depends on the symbol inside the block: load the whole row (at most 8
+                // words) together with the block instead of after it -- one memory round trip per LF step instead of two.
+                // The kernel is a chain of dependent loads (ncu: 89 % of the warp samples on the long scoreboard, a warp
+                // walks as long as its longest lane: 5.3 steps on average at sampling ratio 2).
+                const unsigned long long* rw = reinterpret_cast<const unsigned long long*>(e + ix.ilv_ck_off);   // 8-byte aligned
+                const uint32_t pairs = (ix.symbol_count + 1) >> 1;
+                unsigned long long r2[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) if (i < pairs) r2[i] = __ldg(rw + i);
+                s = b.symidx_of(rem);
+                const unsigned long long pair = s < 4 ? (s < 2 ? r2[0] : r2[1]) : (s < 6 ? r2[2] : r2[3]);
+                ck = (P)((s & 1u) ? (uint32_t)(pair >> 32) : (uint32_t)pair);
+            } else {
+                s = b.symidx_of(rem);
+                ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
+            }
         } else {
             b.load(ix.blocks, q);
             s = b.symidx_of(rem);
