@@ -1487,7 +1487,7 @@ int svfm_index_memory(svfm_index* ix, uint64_t out[5]) {
         for (const DeviceBuffer* b : {&s->pats, &s->offs, &s->unpacked, &s->sp, &s->cnt, &s->counts_out, &s->woffs, &s->out_offs, &s->offs64,
                                       &s->positions, &s->positions_alt, &s->cub_temp, &s->keys0, &s->keys1, &s->vals0, &s->vals1, &s->pay0,
                                       &s->pay1, &s->items0, &s->items1, &s->sweep_hist, &s->sweep_desc, &s->rec_key, &s->rec_key_alt, &s->first,
-                                      &s->sb_hist, &s->sb_base, &s->sb_cursor, &s->sb_recs, &s->resolved, &s->scan_desc,
+                                      &s->sb_hist, &s->sb_base, &s->sb_cursor, &s->sb_recs, &s->resolved,
                                       &s->heavy_sp, &s->heavy_cnt, &s->heavy_obase, &s->heavy_pat, &s->heavy_offs})
             scratch += b->cap;
     for (const svfm_uploader* u : ix->up_pool) scratch += u->pats.cap + u->offs.cap;
