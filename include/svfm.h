@@ -99,8 +99,8 @@ void svfm_free(svfm_index* ix);
 int svfm_index_info(const svfm_index* ix, svfm_info* out);
 /* Device memory held by the handle, in bytes: out[0] the blob copy, out[1] the extended k-mer table, out[2] the
  * interleaved occ copy, out[3] scratch arenas of the idle sessions / upload staging (grow-only until svfm_free),
- * out[4] the packed text copy. */
-int svfm_index_memory(svfm_index* ix, uint64_t out[5]);
+ * out[4] the packed text copy, out[5] the expanded suffix array. */
+int svfm_index_memory(svfm_index* ix, uint64_t out[6]);
 /* Host-only part of load: validate + report sizes without touching a device (LoadError paths). */
 int svfm_check_blob(const uint8_t* blob, size_t blob_len, svfm_type t, svfm_info* out, uint64_t err_detail[2]);
 
@@ -221,9 +221,16 @@ void svfm_host_free(void* p);
  *                      0 = never) mark it persisting in L2 for all their kernels (cudaAccessPolicyWindow).  The default
  *                      2 GiB table is never pinned; this serves deployments that cap SVFM_TUNE_EXT_BITS (env SVFM_L2_PERSIST).
  * SVFM_TUNE_OWN_RADIX: the sweep search sorts its items by table index with this library's radix_pass_kernel (1) or with
- *                      cub::DeviceRadixSort (0, the default: measured 0.84 against 1.36 ms per pass; env SVFM_OWN_RADIX). */
+ *                      cub::DeviceRadixSort (0, the default: measured 0.84 against 1.36 ms per pass; env SVFM_OWN_RADIX).
+ * SVFM_TUNE_FULL_SA  : indexes loaded from now on whose blob samples the suffix array (ratio > 1) also get the EXPANDED
+ *                      suffix array -- the text position of every SA row (4 bytes per text symbol below 2^32 symbols, else
+ *                      8), derived from the blob at load by walking every row once -- when it takes at most 1/8 of the
+ *                      device memory still free.  `locate` then reads one entry per row instead of LF-walking to a sampled
+ *                      row (suffix_array/mod.rs:100-105 trades memory for that walk; a B200 has the memory).  1 (default) /
+ *                      0 = never (env SVFM_FULL_SA).  Results never depend on it. */
 enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
-       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9, SVFM_TUNE_OWN_RADIX = 10 };
+       SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9, SVFM_TUNE_OWN_RADIX = 10,
+       SVFM_TUNE_FULL_SA = 11 };
 #define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */

@@ -53,6 +53,10 @@ struct DevIndex {
     // rank among the occurring symbols, text_bits (1, 2, 4 or 8) bits each, little-endian inside 32-bit words; NULL = not built
     const uint32_t* text;
     uint32_t text_bits;
+    // expanded suffix array derived from the blob at load (search_kernels.cuh, "expanded suffix array"): the text position
+    // of EVERY SA row, 32-bit entries when the text is shorter than 2^32 symbols (fsa32), else P; NULL = not built
+    const void* fsa;
+    uint32_t fsa32;
 };
 
 // the symbol maps alone (kernels that do not touch the index arrays)
@@ -106,6 +110,13 @@ struct Block {
     using T = VecTraits<VBITS>;
     using W = typename T::W;
     W w[NPL][T::WORDS];
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int v = 0; v < NPL; v++)
+#pragma unroll
+            for (int k = 0; k < T::WORDS; k++) w[v][k] = 0;
+    }
 
     // In-place load from the blob's `blocks` section.  Blocks are only 8-byte aligned there (an odd word count puts every
     // other block on an odd word), so 64-bit words are fetched one by one; 16-byte window loads + a conditional shift were

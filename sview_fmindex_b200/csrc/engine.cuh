@@ -44,6 +44,9 @@ struct svfm_index {
     uint32_t* d_text = nullptr;    // packed text copy (text verification), or NULL
     uint32_t text_bits = 0;
     uint64_t text_bytes = 0;
+    void* d_fsa = nullptr;         // expanded suffix array (text position of every SA row), or NULL
+    uint32_t fsa32 = 0;            // its entries are 32 bits wide
+    uint64_t fsa_bytes = 0;
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
     std::vector<svfm_uploader*> up_pool;  // idle uploaders
@@ -123,6 +126,8 @@ static DevIndex<P> make_dev_index(const svfm_index* ix) {
     d.ilv_ck_off = ix->ilv_ck_off;
     d.text = ix->d_text;
     d.text_bits = ix->text_bits;
+    d.fsa = ix->d_fsa;
+    d.fsa32 = ix->fsa32;
     return d;
 }
 
@@ -262,9 +267,44 @@ static int run_small(svfm_session* s, const PatternBatch& pb, const SmallOut& ou
     return SVFM_OK;
 }
 
-// Packed text copy for the text verification (search_kernels.cuh), built once per index after the interleaved occ copy.
+// Expanded suffix array (search_kernels.cuh), built once per index after the interleaved occ copy and before the text copy
+// (whose construction then reads it instead of walking every row again).  Optional: skipped when it would take more than
+// 1/8 of the device memory still free.
+extern std::atomic<uint64_t> g_full_sa, g_text;   // svfm_api.cu (SVFM_TUNE_FULL_SA, SVFM_TUNE_TEXT)
+template <class P, int NPL, int VBITS>
+static int run_build_fsa(svfm_index* ix) {
+    const uint64_t n = ix->text_len;
+    if (!g_full_sa.load() || n == 0 || ix->L.sampling_ratio <= 1) return SVFM_OK;   // ratio 1: the blob's array is complete already
+    const bool e32 = sizeof(P) == 4 || n < 0xffffffffull;
+    const uint64_t bytes = (n + 1) * (e32 ? 4 : 8);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 8) { (void)cudaGetLastError(); return SVFM_OK; }
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { (void)cudaGetLastError(); return SVFM_OK; }   // optional structure
+    const DevIndex<P> dix = make_dev_index<P>(ix);   // ix->d_fsa is still NULL: the walk uses the sampled array
+    const int grid = grid_for(n, 256, ix->device) * 4;
+    if (e32) {
+        if (dix.ilv) fsa_build_kernel<P, NPL, VBITS, true, uint32_t><<<grid, 256>>>(dix, n, (uint32_t*)d);
+        else fsa_build_kernel<P, NPL, VBITS, false, uint32_t><<<grid, 256>>>(dix, n, (uint32_t*)d);
+    } else {
+        if (dix.ilv) fsa_build_kernel<P, NPL, VBITS, true, unsigned long long><<<grid, 256>>>(dix, n, (unsigned long long*)d);
+        else fsa_build_kernel<P, NPL, VBITS, false, unsigned long long><<<grid, 256>>>(dix, n, (unsigned long long*)d);
+    }
+    g_launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); SVFM_CUDA(e); }
+    ix->d_fsa = d;
+    ix->fsa32 = e32 ? 1 : 0;
+    ix->fsa_bytes = bytes;
+    return SVFM_OK;
+}
+
+// Packed text copy for the text verification (search_kernels.cuh), built once per index after the expanded suffix array.
 template <class P, int NPL, int VBITS>
 static int run_build_text(svfm_index* ix) {
+    int rc = run_build_fsa<P, NPL, VBITS>(ix);
+    if (rc) return rc;
+    if (!g_text.load()) return SVFM_OK;
     const uint64_t s_eff = ix->symbols_present;
     const uint64_t n = ix->text_len;
     if (s_eff < 1 || n == 0) return SVFM_OK;

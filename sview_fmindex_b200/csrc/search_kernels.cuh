@@ -71,7 +71,7 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sy
     rank_addr<P, VBITS>(ix, sp, q0, r0);
     rank_addr<P, VBITS>(ix, ep, q1, r1);
     B b0, b1;
-    P ck0, ck1;
+    P ck0, ck1 = 0;
     if constexpr (ILV) {
         const uint8_t* e0 = ix.ilv + (uint64_t)q0 * ix.ilv_stride;
         ck0 = ld_gather<P>(reinterpret_cast<const P*>(e0 + ix.ilv_ck_off) + sym);
@@ -80,9 +80,12 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sy
         ck0 = ld_gather<P>(ix.rank_checkpoints + ((uint64_t)q0 * ix.symbol_count + sym));
         b0.load(ix.blocks, q0);
     }
-    b1 = b0;
-    ck1 = ck0;
-    if (q1 != q0) {
+    // The second block goes into registers of its own (cleared, not copied from b0): a predicated load into a copy of b0
+    // has to wait for b0's load to land first, which serialised the two fetches (ncu: a quarter of the round kernel's
+    // stall samples sat on that copy).
+    const bool two = q1 != q0;
+    b1.clear();
+    if (two) {
         if constexpr (ILV) {
             const uint8_t* e1 = ix.ilv + (uint64_t)q1 * ix.ilv_stride;
             ck1 = ld_gather<P>(reinterpret_cast<const P*>(e1 + ix.ilv_ck_off) + sym);
@@ -94,11 +97,13 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sy
     }
     typename B::W flip[NPL];
     B::flips(sym, flip);
-    typename B::W m[VecTraits<VBITS>::WORDS];
-    b0.match_flips(flip, m);
-    sp = (P)(c + ck0 + (P)B::prefix_count(m, r0));
-    b1.match_flips(flip, m);
-    ep = (P)(c + ck1 + (P)B::prefix_count(m, r1));
+    typename B::W m0[VecTraits<VBITS>::WORDS], m1[VecTraits<VBITS>::WORDS];
+    b0.match_flips(flip, m0);
+    b1.match_flips(flip, m1);
+    sp = (P)(c + ck0 + (P)B::prefix_count(m0, r0));
+#pragma unroll
+    for (int k = 0; k < VecTraits<VBITS>::WORDS; k++) m1[k] = two ? m1[k] : m0[k];
+    ep = (P)(c + (two ? ck1 : ck0) + (P)B::prefix_count(m1, r1));
     SVFM_ASSERT(sp <= ep);   // ranks are monotone (with_slice.rs:27: the loop condition relies on it)
 }
 
@@ -151,56 +156,77 @@ struct SearchIO {
 // FmIndex::write_locations_to_buffer (locate/mod.rs:14-37) for ONE SA row: LF-walk to the nearest
 // sampled row (BwmView::get_pre_rank_and_symidx, bwm/mod.rs:217-236), then
 // SuffixArrayView::get_location_of (suffix_array/mod.rs:100-105).
+// One LF step from SA row `pos` (not the row of the sentinel): BwmView::get_pre_rank_and_symidx (bwm/mod.rs:217-236) followed
+// by count_array[s] + rank, i.e. the row of the suffix that starts one text position earlier.
+template <class P, int NPL, int VBITS, bool ILV>
+__device__ __forceinline__ P lf_step(const DevIndex<P>& ix, const P* __restrict__ s_count, P pos) {
+    uint64_t q;
+    uint32_t rem;
+    rank_addr<P, VBITS>(ix, pos, q, rem);
+    Block<NPL, VBITS> b;
+    P ck;
+    uint32_t s;
+    if constexpr (ILV) {
+        const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
+        b.load_aligned(e);
+        if (sizeof(P) == 4 && ix.symbol_count <= 8 && (ix.ilv_ck_off & 7u) == 0) {   // (row end stays inside the slot: DESIGN.md)
+            // Which checkpoint word is needed depends on the symbol inside the block: load the whole row (at most 8
+            // words) together with the block instead of after it -- one memory round trip per LF step instead of two.
+            const unsigned long long* rw = reinterpret_cast<const unsigned long long*>(e + ix.ilv_ck_off);   // 8-byte aligned
+            const uint32_t pairs = (ix.symbol_count + 1) >> 1;
+            unsigned long long r2[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) if (i < pairs) r2[i] = __ldg(rw + i);
+            s = b.symidx_of(rem);
+            const unsigned long long pair = s < 4 ? (s < 2 ? r2[0] : r2[1]) : (s < 6 ? r2[2] : r2[3]);
+            ck = (P)((s & 1u) ? (uint32_t)(pair >> 32) : (uint32_t)pair);
+        } else {
+            s = b.symidx_of(rem);
+            ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
+        }
+    } else {
+        b.load(ix.blocks, q);
+        s = b.symidx_of(rem);
+        ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
+    }
+    SVFM_ASSERT(s < ix.symbol_count);
+    return (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
+}
+
+// Is SA row `pos` sampled (pos % sampling_ratio == 0)?  quot = pos / sampling_ratio.
+template <class P>
+__device__ __forceinline__ bool sa_sampled(const DevIndex<P>& ix, P pos, uint64_t& quot) {
+    if (ix.ratio_mask != 0xffffffffu) {
+        quot = (uint64_t)pos >> ix.ratio_shift;
+        return ((uint32_t)pos & ix.ratio_mask) == 0;
+    }
+    quot = (uint64_t)pos / ix.sampling_ratio;
+    return quot * ix.sampling_ratio == (uint64_t)pos;
+}
+
+// ---- expanded suffix array ----------------------------------------------------------------------------------------------
+// The blob samples the suffix array (every r-th row) because the reference trades CPU memory for LF-walk time
+// (suffix_array/mod.rs:43-70, :100-105).  A B200 has 180 GB: at load the engine walks every row ONCE (fsa_build_kernel:
+// locate_row on the sampled array) and keeps the text position of all rows next to the blob -- 4 bytes per text symbol,
+// built only when that is a small share of the free device memory (SVFM_TUNE_FULL_SA).  `locate` then costs one read per
+// row instead of 1 + (r-1)/2 .. r dependent random cache lines, and a batch in SA order reads the array as a stream.
+// Results are identical by construction: the entries ARE what locate/mod.rs:21-33 computes for that row.
+template <class P>
+__device__ __forceinline__ P fsa_get(const DevIndex<P>& ix, P row) {
+    if (sizeof(P) == 4 || ix.fsa32) return (P)__ldg(reinterpret_cast<const uint32_t*>(ix.fsa) + row);
+    return (P)__ldg(reinterpret_cast<const unsigned long long*>(ix.fsa) + row);
+}
+
 template <class P, int NPL, int VBITS, bool ILV>
 __device__ __forceinline__ P locate_row(const DevIndex<P>& ix, const P* __restrict__ s_count, P pos) {
+    if (ix.fsa) return fsa_get<P>(ix, pos);
     P offset = 0;
     for (;;) {
-        // pos % sampling_ratio != 0
         uint64_t quot;
-        bool sampled;
-        if (ix.ratio_mask != 0xffffffffu) {
-            sampled = ((uint32_t)pos & ix.ratio_mask) == 0;
-            quot = (uint64_t)pos >> ix.ratio_shift;
-        } else {
-            quot = (uint64_t)pos / ix.sampling_ratio;
-            sampled = (quot * ix.sampling_ratio == (uint64_t)pos);
-        }
-        if (sampled) return (P)(ld_gather<P>(ix.suffix_array + quot) + offset);
+        if (sa_sampled<P>(ix, pos, quot)) return (P)(ld_gather<P>(ix.suffix_array + quot) + offset);
         if (pos == (P)(ix.sentinel_index - 1)) return offset;  // None arm, locate/mod.rs:27-30
-        uint64_t q;
-        uint32_t rem;
-        rank_addr<P, VBITS>(ix, pos, q, rem);
-        Block<NPL, VBITS> b;
-        P ck;
-        uint32_t s;
-        if constexpr (ILV) {
-            const uint8_t* e = ix.ilv + q * ix.ilv_stride;  // block and checkpoint row arrive with one fetch
-            b.load_aligned(e);
-            if (sizeof(P) == 4 && ix.symbol_count <= 8 && (ix.ilv_ck_off & 7u) == 0) {   // (row end stays inside the slot: DESIGN.md)
-                // Which checkpoint word is needed depends on the symbol inside the block: load the whole row (at most 8
-                // words) together with the block instead of after it -- one memory round trip per LF step instead of two.
-                // The kernel is a chain of dependent loads (ncu: 89 % of the warp samples on the long scoreboard, a warp
-                // walks as long as its longest lane: 5.3 steps on average at sampling ratio 2).
-                const unsigned long long* rw = reinterpret_cast<const unsigned long long*>(e + ix.ilv_ck_off);   // 8-byte aligned
-                const uint32_t pairs = (ix.symbol_count + 1) >> 1;
-                unsigned long long r2[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (uint32_t i = 0; i < 4; i++) if (i < pairs) r2[i] = __ldg(rw + i);
-                s = b.symidx_of(rem);
-                const unsigned long long pair = s < 4 ? (s < 2 ? r2[0] : r2[1]) : (s < 6 ? r2[2] : r2[3]);
-                ck = (P)((s & 1u) ? (uint32_t)(pair >> 32) : (uint32_t)pair);
-            } else {
-                s = b.symidx_of(rem);
-                ck = ld_gather<P>(reinterpret_cast<const P*>(e + ix.ilv_ck_off) + s);
-            }
-        } else {
-            b.load(ix.blocks, q);
-            s = b.symidx_of(rem);
-            ck = ld_gather<P>(ix.rank_checkpoints + q * ix.symbol_count + s);
-        }
-        pos = (P)(s_count[s] + ck + (P)b.remain_count(rem, s));  // remain_count(0, .) == 0
+        pos = lf_step<P, NPL, VBITS, ILV>(ix, s_count, pos);
         offset += 1;
-        SVFM_ASSERT(s < ix.symbol_count);
     }
 }
 
@@ -469,6 +495,18 @@ static __global__ void ilv_build_kernel(const uint32_t* __restrict__ blocks, uin
 // Row r of the suffix array: its suffix starts at text position locate_row(r), and the BWT symbol of the row is the text
 // symbol right before it.  One thread per row; the symbol (as its rank among the occurring symbols) is OR-ed into the
 // zeroed packed array.
+// Expanded suffix array: fsa[row] = text position of SA row `row`, for every row (ix.fsa must be NULL here: the walk uses
+// the blob's sampled array).
+template <class P, int NPL, int VBITS, bool ILV, class E>
+__global__ void __launch_bounds__(256)
+fsa_build_kernel(const DevIndex<P> ix, uint64_t n, E* __restrict__ fsa) {
+    __shared__ P s_count[65];
+    for (int i = threadIdx.x; i <= (int)ix.symbol_count; i += blockDim.x) s_count[i] = ix.count_array[i];
+    __syncthreads();
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+        fsa[r] = (E)locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)r);
+}
+
 template <class P, int NPL, int VBITS, bool ILV>
 __global__ void __launch_bounds__(256)
 text_build_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t* __restrict__ text) {
@@ -705,15 +743,57 @@ pack_sweep_kernel(const uint8_t* __restrict__ table, const DevSyms syms, const P
     if (errbits) atomicOr(err, errbits);
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+// Look-back descriptors are single words (flag | count) and carry no other data, so relaxed accesses are enough; GPU scope
+// keeps the polls inside the device's L2 (ld.volatile compiles to a SYSTEM-scope strong load on sm_100: measured slower).
+#ifndef SVFM_DESC_GPU
+#define SVFM_DESC_GPU 1
+#endif
+__device__ __forceinline__ uint32_t ld_desc(const uint32_t* p) {
     uint32_t v;
+#if SVFM_DESC_GPU
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
-__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+__device__ __forceinline__ void st_desc(uint32_t* p, uint32_t v) {
+#if SVFM_DESC_GPU
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 constexpr uint32_t DESC_AGG = 1u << 30, DESC_PREFIX = 2u << 30, DESC_MASK = (1u << 30) - 1;
+
+// Decoupled look-back for one digit: the sum of the digit's counts over the tiles [0, tile) = the aggregates of the
+// predecessors back to the nearest one that has published its inclusive prefix.  LB_WINDOW descriptors are requested per
+// trip before any of them is consumed, so a walk of k tiles costs ~k / LB_WINDOW L2 round trips instead of k.
+#ifndef SVFM_LB_WINDOW
+#define SVFM_LB_WINDOW 4
+#endif
+constexpr int LB_WINDOW = SVFM_LB_WINDOW;
+__device__ __forceinline__ uint32_t lookback_excl(const uint32_t* desc, uint64_t tile, uint32_t nbins, uint32_t b) {
+    uint32_t excl = 0;
+    uint64_t t = tile;   // the descriptors of the tiles below t are still to be read
+    while (t > 0) {
+        uint32_t v[LB_WINDOW];
+#pragma unroll
+        for (int l = 0; l < LB_WINDOW; l++) v[l] = (uint64_t)l < t ? ld_desc(desc + (t - 1 - l) * nbins + b) : DESC_PREFIX;
+        bool done = false;
+#pragma unroll
+        for (int l = 0; l < LB_WINDOW; l++) {
+            if (!done) {
+                while ((v[l] >> 30) == 0) v[l] = ld_desc(desc + (t - 1 - l) * nbins + b);
+                excl += v[l] & DESC_MASK;
+                done = (v[l] >> 30) == 2u;
+            }
+        }
+        if (done) break;
+        t = t > (uint64_t)LB_WINDOW ? t - LB_WINDOW : 0;
+    }
+    return excl;
+}
 
 // ---- one stable LSD radix pass over the packed items (table index -> payload), 8-bit digit ---------------------------------
 // The sort of the sweep items by table index runs on this kernel (round 1 used cub::DeviceRadixSort): the same building
@@ -797,16 +877,11 @@ radix_pass_kernel(const uint32_t* __restrict__ key_in, const SweepPay<R>* __rest
                 s_whist[w * RADIX_BINS + b] = acc;
                 acc += t;
             }
-            st_volatile_u32(desc + tile * RADIX_BINS + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+            st_desc(desc + tile * RADIX_BINS + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
             uint32_t excl = 0;
             if (tile > 0) {
-                for (uint64_t t = tile - 1;; t--) {
-                    uint32_t v;
-                    do { v = ld_volatile_u32(desc + t * RADIX_BINS + b); } while ((v >> 30) == 0);
-                    excl += v & DESC_MASK;
-                    if ((v >> 30) == 2u || t == 0) break;
-                }
-                st_volatile_u32(desc + tile * RADIX_BINS + b, DESC_PREFIX | (excl + acc));
+                excl = lookback_excl(desc, tile, RADIX_BINS, b);
+                st_desc(desc + tile * RADIX_BINS + b, DESC_PREFIX | (excl + acc));
             }
             // exclusive scan of the tile totals over the digits: where the digit's run starts inside the exchange buffer
             uint32_t incl = acc;
@@ -866,15 +941,17 @@ constexpr int ROUND_THREADS = SVFM_ROUND_THREADS;
 #ifndef SVFM_ROUND_MIN_CTAS
 #define SVFM_ROUND_MIN_CTAS 5
 #endif
-#ifndef SVFM_ROUND_LB
-#define SVFM_ROUND_LB 0
+#ifndef SVFM_ROUND_LBWARP
+#define SVFM_ROUND_LBWARP 1
 #endif
+// ROUND_LBWARP: the last warp of the CTA carries no items; it computes the tile's digit totals, publishes them and walks the
+// look-back WHILE the other warps run their backward steps (the look-back is a chain of dependent L2 round trips; with all
+// warps waiting for it behind a barrier it cost a quarter of every tile's time: ncu, barrier stall 5.4 per issue slot).
+constexpr bool ROUND_LBWARP = SVFM_ROUND_LBWARP != 0;
 constexpr int ROUND_ITEMS = SVFM_ROUND_ITEMS;               // items per thread
-constexpr int ROUND_TILE = ROUND_THREADS * ROUND_ITEMS;     // items per tile
-constexpr int ROUND_WARPS = ROUND_THREADS / 32;
+constexpr int ROUND_WARPS = ROUND_THREADS / 32 - (ROUND_LBWARP ? 1 : 0);   // warps that carry items
+constexpr int ROUND_TILE = ROUND_WARPS * 32 * ROUND_ITEMS;  // items per tile
 constexpr int ROUND_MAX_BINS = 512;
-constexpr int ROUND_LB = SVFM_ROUND_LB;                     // look-back: descriptors polled per thread and step (0: one
-                                                            // thread per digit walks back alone -- measured faster, see below)
 enum : int { PART_NONE = 0, PART_SYMBOLS = 1, PART_INDEX = 2 };
 
 template <class P, class R>
@@ -909,10 +986,10 @@ struct SweepRoundIO {
 //   so that every digit's run is written with coalesced stores.
 // PART_SYMBOLS: digit = the symbols just consumed, last one most significant; exclusive prefix of the digit counts over all
 //   earlier tiles by decoupled look-back (one descriptor word per tile and digit: flag | count).  The digit depends on the
-//   pattern alone, so a tile publishes its counts BEFORE its backward steps.  With ROUND_LB > 0 the look-back polls a
-//   WINDOW of predecessors at once (256 / nbins threads per digit, ROUND_LB descriptors each); measured on B200 (10^8
-//   20-mers, two rounds): 5.83 ms with a window of 8 against 5.31 ms for one thread per digit walking back alone (16.6
-//   polls per tile on average) -- the two extra block barriers per window cost more than the shorter walk saves.
+//   pattern alone, so a tile publishes its counts BEFORE its backward steps, and (ROUND_LBWARP) a warp without items
+//   walks the look-back while the other warps run theirs; the walk requests LB_WINDOW descriptors per trip (lookback_excl).
+//   History (B200, 10^8 20-mers, two rounds): every thread waiting behind a barrier for one thread per digit walking back
+//   one descriptor at a time 5.31 ms; a block-wide window of 8 predecessors with two extra barriers per window 5.83 ms.
 //   With io.bin_cursor set, PART_SYMBOLS skips the look-back: a tile reserves its space inside every digit's run with one
 //   atomic add per digit, so the tiles of a run follow each other in ARRIVAL order instead of tile order.  Results never
 //   depend on the order of the work items; the runs stay sorted up to the few hundred tiles in flight at any time (each
@@ -930,9 +1007,8 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
     __shared__ P s_count[65];
     __shared__ uint8_t s_present[64];
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_scan[ROUND_WARPS];
-    __shared__ uint64_t s_wsum[ROUND_WARPS];
-    __shared__ uint32_t s_lb[ROUND_THREADS * (ROUND_LB > 0 ? ROUND_LB : 1)];
+    __shared__ uint32_t s_scan[ROUND_THREADS / 32];
+    __shared__ uint64_t s_wsum[ROUND_THREADS / 32];
     // dynamic: items[ROUND_TILE] | gbase[nbins] (u64) | binstart[nbins] (u64) | whist[ROUND_WARPS][nbins] | tilebin[nbins]
     Item* s_items = reinterpret_cast<Item*>(s_dyn);
     uint64_t* s_gbase = reinterpret_cast<uint64_t*>(s_dyn + sizeof(Item) * ROUND_TILE);
@@ -989,27 +1065,45 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
         const uint64_t tile = s_tile;
         __syncthreads();  // everyone has read s_tile before thread 0 can overwrite it
         if (tile >= n_tiles) break;
-        const uint64_t base = tile * ROUND_TILE + (uint64_t)warp * (32 * ROUND_ITEMS) + lane;
+        const bool worker = warp < (uint32_t)ROUND_WARPS;
+        const uint64_t base = worker ? tile * ROUND_TILE + (uint64_t)warp * (32 * ROUND_ITEMS) + lane : n;   // look-back warp: no items
         P sp[ROUND_ITEMS], cnt[ROUND_ITEMS];
         R rest[ROUND_ITEMS];
         uint32_t idx[ROUND_ITEMS];
-        // ---- load (warp-striped: row k of a warp is 32 consecutive items)
+        // ---- load (warp-striped: row k of a warp is 32 consecutive items).  FIRST: all table indices first, then all
+        // table entries (one 8/16-byte load each), so that a thread has its four dependent lookups in flight together.
+        if constexpr (FIRST) {
+            uint32_t e[ROUND_ITEMS];
 #pragma unroll
-        for (int k = 0; k < ROUND_ITEMS; k++) {
-            const uint64_t w = base + (uint64_t)k * 32;
-            sp[k] = 0; cnt[k] = 0; rest[k] = 0; idx[k] = 0;
-            if (w < n) {
-                if (FIRST) {
-                    const uint32_t e = io.prefix[w];
+            for (int k = 0; k < ROUND_ITEMS; k++) {
+                const uint64_t w = base + (uint64_t)k * 32;
+                e[k] = 0xffffffffu; rest[k] = 0; idx[k] = 0;
+                if (w < n) {
+                    e[k] = io.prefix[w];
                     const SweepPay<R> v = io.pay[w];
                     rest[k] = v.rest;
                     idx[k] = v.idx;
-                    if (e != 0xffffffffu) {
-                        const P* q = ix.ext + 2 * (uint64_t)e;
-                        sp[k] = __ldg(q);
-                        cnt[k] = __ldg(q + 1);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < ROUND_ITEMS; k++) {
+                sp[k] = 0; cnt[k] = 0;
+                if (e[k] != 0xffffffffu) {
+                    if constexpr (sizeof(P) == 4) {
+                        const uint2 q = __ldg(reinterpret_cast<const uint2*>(ix.ext) + e[k]);
+                        sp[k] = q.x; cnt[k] = q.y;
+                    } else {
+                        const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2*>(ix.ext) + e[k]);
+                        sp[k] = (P)q.x; cnt[k] = (P)q.y;
                     }
-                } else {
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ROUND_ITEMS; k++) {
+                const uint64_t w = base + (uint64_t)k * 32;
+                sp[k] = 0; cnt[k] = 0; rest[k] = 0; idx[k] = 0;
+                if (w < n) {
                     const Item v = io.items_in[w];
                     sp[k] = v.sp; cnt[k] = v.cnt; rest[k] = v.rest; idx[k] = v.idx;
                 }
@@ -1039,9 +1133,12 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 __syncwarp();
             }
             __syncthreads();
-            // per digit: offsets of the warps inside the tile, tile total -> descriptor (aggregate)
-            for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
+        }
+        // per digit: offsets of the warps inside the tile, tile total -> descriptor (aggregate) or atomic reservation
+        auto aggregate = [&](uint32_t b0, uint32_t stride) {
+            for (uint32_t b = b0; b < nbins; b += stride) {
                 uint32_t acc = 0;
+#pragma unroll
                 for (int w = 0; w < ROUND_WARPS; w++) {
                     const uint32_t t = s_whist[w * nbins + b];
                     s_whist[w * nbins + b] = acc;
@@ -1049,11 +1146,29 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 }
                 s_tilebin[b] = acc;
                 if (PART == PART_SYMBOLS && !io.bin_cursor)
-                    st_volatile_u32(io.desc + tile * nbins + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
+                    st_desc(io.desc + tile * nbins + b, (tile > 0 ? DESC_AGG : DESC_PREFIX) | acc);
                 else
                     s_gbase[b] = s_binstart[b] + (acc ? atomicAdd(io.bin_cursor + b, acc) : 0u);
             }
-        }
+        };
+        // look-back over the earlier tiles (decoupled: aggregate or inclusive prefix per tile and digit), one thread per digit
+        auto lookback = [&](uint32_t b0, uint32_t stride) {
+            for (uint32_t b = b0; b < nbins; b += stride) {
+                uint32_t excl = 0;
+                if (tile > 0) {
+                    excl = lookback_excl(io.desc, tile, nbins, b);
+                    SVFM_ASSERT((uint64_t)excl <= n);
+                    st_desc(io.desc + tile * nbins + b, DESC_PREFIX | (excl + s_tilebin[b]));
+                }
+                s_gbase[b] = s_binstart[b] + excl;
+            }
+        };
+        const bool lb_needed = PART == PART_SYMBOLS && !io.bin_cursor;
+        if constexpr (PART != PART_NONE && !ROUND_LBWARP) aggregate(threadIdx.x, ROUND_THREADS);
+        if (PART != PART_NONE && ROUND_LBWARP && !worker) {
+            aggregate(lane, 32);
+            if (lb_needed) lookback(lane, 32);
+        } else {
         // ---- backward steps
 #pragma unroll
         for (int k = 0; k < ROUND_ITEMS; k++) {
@@ -1072,6 +1187,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 rows += (unsigned long long)cnt[k];
             }
         }
+        }
         if constexpr (PART == PART_NONE) {
 #pragma unroll
             for (int k = 0; k < ROUND_ITEMS; k++) {
@@ -1084,56 +1200,7 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 }
             }
         } else {
-        if (PART == PART_SYMBOLS && !io.bin_cursor) {
-        // ---- look-back over the earlier tiles (decoupled: aggregate or inclusive prefix per tile and digit)
-        if (ROUND_LB > 0 && nbins <= (uint32_t)ROUND_THREADS) {
-            // thread (b, j) polls the predecessors at distance j+1, j+1+W, ... of the window for digit b (W threads per digit)
-            const uint32_t b = threadIdx.x & (nbins - 1u), j = threadIdx.x / nbins, W = ROUND_THREADS / nbins;
-            uint32_t excl = 0;
-            bool done = tile == 0;
-            for (uint64_t far = 0; tile > 0; far += (uint64_t)W * ROUND_LB) {  // predecessors tile-1-far .. tile-far-W*LB
-#pragma unroll
-                for (int l = 0; l < ROUND_LB; l++) {
-                    const uint64_t d = far + j + (uint64_t)l * W;  // distance - 1
-                    uint32_t v = DESC_PREFIX;                       // before tile 0: an empty prefix
-                    if (d < tile) {
-                        const uint32_t* q = io.desc + (tile - 1 - d) * nbins + b;
-                        do { v = ld_volatile_u32(q); } while ((v >> 30) == 0);
-                    }
-                    s_lb[(j + l * W) * nbins + b] = v;
-                }
-                __syncthreads();
-                if (j == 0 && !done) {
-                    for (uint32_t d = 0; d < W * ROUND_LB; d++) {
-                        const uint32_t v = s_lb[d * nbins + b];
-                        excl += v & DESC_MASK;
-                        if ((v >> 30) == 2u) { done = true; break; }
-                    }
-                }
-                if (__syncthreads_and(j != 0 || done)) break;
-            }
-            if (j == 0) {
-                if (tile > 0) st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + s_tilebin[b]));
-                s_gbase[b] = s_binstart[b] + excl;
-            }
-        } else {
-            for (uint32_t b = threadIdx.x; b < nbins; b += ROUND_THREADS) {
-                uint32_t excl = 0;
-                const uint32_t acc = s_tilebin[b];
-                if (tile > 0) {
-                    for (uint64_t t = tile - 1;; t--) {
-                        uint32_t v;
-                        do { v = ld_volatile_u32(io.desc + t * nbins + b); } while ((v >> 30) == 0);
-                        excl += v & DESC_MASK;
-                        SVFM_ASSERT((uint64_t)excl <= n);
-                        if ((v >> 30) == 2u || t == 0) break;
-                    }
-                    st_volatile_u32(io.desc + tile * nbins + b, DESC_PREFIX | (excl + acc));
-                }
-                s_gbase[b] = s_binstart[b] + excl;
-            }
-        }
-        }
+        if constexpr (!ROUND_LBWARP) { if (lb_needed) lookback(threadIdx.x, ROUND_THREADS); }
         __syncthreads();
         // exclusive scan of the tile totals over the digits (position of every digit's run inside the exchange buffer)
         {
@@ -1309,6 +1376,9 @@ small_batch_kernel(const DevIndex<P> ix, const PatternBatch pb, const SmallOut o
 }
 
 constexpr int LOCATE_THREADS = 256;
+#ifndef SVFM_LOCATE_MIN_CTAS
+#define SVFM_LOCATE_MIN_CTAS 1
+#endif
 
 template <class P>
 struct HeavyList {
@@ -1349,7 +1419,7 @@ struct BucketOut {
 // rows does not serialise one lane.  Patterns with more than HEAVY_ROWS rows are deferred to
 // locate_rows_kernel through the heavy list.
 template <class P, int NPL, int VBITS, bool ILV, bool BUCKET>
-__global__ void __launch_bounds__(LOCATE_THREADS)
+__global__ void __launch_bounds__(LOCATE_THREADS, SVFM_LOCATE_MIN_CTAS)
 locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
                    const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
                    P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy, BucketOut<P> bk,
@@ -1359,74 +1429,137 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t w0 = warp_id * 32; w0 < n; w0 += n_warps * 32) {
-        const uint64_t w = w0 + lane;
-        uint32_t c = 0;
-        P sp = 0;
-        uint64_t obase = 0;
-        uint32_t pat = 0;
-        bool res = false;   // sp is the text position already (text verification)
-        if (w < n) {
-            const P cw = cnt_work[w];
-            if (cw != 0) {
-                sp = sp_work[w];
-                res = resolved && resolved[w];
-                pat = idx ? idx[w] : (uint32_t)w;
-                if constexpr (BUCKET) obase = atomicAdd(bk.cursor + (pat >> SB_SHIFT), (unsigned long long)cw);
-                else obase = offs[w];
-                if ((uint64_t)cw > HEAVY_ROWS) {
-                    const unsigned long long h = atomicAdd(heavy.n, 1ull);
-                    if (h < heavy.capacity) { heavy.sp[h] = sp; heavy.cnt[h] = cw; heavy.obase[h] = obase; heavy.pat[h] = pat; }
-                } else {
-                    c = (uint32_t)cw;
-                }
-            }
+    const uint64_t groups = (n + 31) / 32;
+    auto emit = [&](uint64_t at, P pos, uint32_t pattern) {
+        if constexpr (BUCKET) {
+            SbRec<P> r;
+            r.pos = pos;
+            r.idx = pattern;
+            if constexpr (sizeof(P) == 8) r.pad = 0;
+            bk.recs[at] = r;
+        } else {
+            positions[at] = pos;
+            if (rec_key) rec_key[at] = pattern;
         }
-        auto emit = [&](uint64_t at, P pos, uint32_t pattern) {
-            if constexpr (BUCKET) {
-                SbRec<P> r;
-                r.pos = pos;
-                r.idx = pattern;
-                if constexpr (sizeof(P) == 8) r.pad = 0;
-                bk.recs[at] = r;
+    };
+    // staged group (two steps ahead of the lanes): raw loads issued (ST_RAW), then slots reserved (ST_READY)
+    enum : int { ST_EMPTY = 0, ST_RAW = 1, ST_READY = 2 };
+    int st = ST_EMPTY;
+    uint64_t g_next = warp_id;
+    uint32_t s_c = 0, s_pat = 0;
+    P s_sp = 0, s_cw = 0;
+    uint64_t s_obase = 0;
+    bool s_res = false;
+    auto stage_load = [&]() {   // issue the loads of group g_next (nothing is consumed here)
+        st = ST_EMPTY;
+        if (g_next < groups) {
+            const uint64_t w = g_next * 32 + lane;
+            s_cw = 0; s_sp = 0; s_pat = (uint32_t)w; s_res = false;
+            if (w < n) {
+                s_cw = cnt_work[w];
+                s_sp = sp_work[w];
+                if (idx) s_pat = idx[w];
+                if (resolved) s_res = resolved[w] != 0;
+            }
+            g_next += n_warps;
+            st = ST_RAW;
+        }
+    };
+    auto stage_reserve = [&]() {   // consume the raw loads: reserve the output slots, defer heavy patterns
+        s_c = 0;
+        if (s_cw != 0) {
+            if constexpr (BUCKET) s_obase = atomicAdd(bk.cursor + (s_pat >> SB_SHIFT), (unsigned long long)s_cw);
+            else s_obase = offs[(g_next - n_warps) * 32 + lane];
+            if ((uint64_t)s_cw > HEAVY_ROWS) {
+                const unsigned long long h = atomicAdd(heavy.n, 1ull);
+                if (h < heavy.capacity) { heavy.sp[h] = s_sp; heavy.cnt[h] = s_cw; heavy.obase[h] = s_obase; heavy.pat[h] = s_pat; }
             } else {
-                positions[at] = pos;
-                if (rec_key) rec_key[at] = pattern;
+                s_c = (uint32_t)s_cw;
             }
-        };
-        if (__all_sync(full, c <= 1u)) {
-            // common case: at most one row per pattern, no redistribution needed
-            if (c) emit(obase, res ? sp : locate_row<P, NPL, VBITS, ILV>(ix, s_count, sp), pat);
-            continue;
         }
-        uint32_t incl = c;
+        st = ST_READY;
+    };
+    // current group: item `lane` of the group has rows [b_incl - b_c, b_incl) of the group's T rows
+    uint32_t b_incl = 0, b_c = 0, b_pat = 0, T = 0, next = 0;
+    P b_sp = 0;
+    uint64_t b_obase = 0;
+    bool b_res = false;
+    // the row this lane is walking
+    bool active = false, res = false;
+    P pos = 0, offset = 0;
+    uint64_t at = 0;
+    uint32_t pat = 0;
+    stage_load();
+    for (;;) {
+        if (st == ST_RAW) stage_reserve();
+        // ---- hand rows to the lanes that have none
+        unsigned fm = __ballot_sync(full, !active);
+        while (fm != 0 && next >= T && st == ST_READY) {   // the current group is used up: install the staged one
+            b_c = s_c; b_sp = s_sp; b_pat = s_pat; b_obase = s_obase; b_res = s_res;
+            b_incl = b_c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(full, incl, d);
-            if ((int)lane >= d) incl += v;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(full, b_incl, d);
+                if ((int)lane >= d) b_incl += v;
+            }
+            T = __shfl_sync(full, b_incl, 31);
+            next = 0;
+            stage_load();
+            if (T == 0 && st == ST_RAW) stage_reserve();   // an empty group: keep going
         }
-        const uint32_t excl = incl - c;
-        const uint32_t total = __shfl_sync(full, incl, 31);
-        for (uint32_t r0 = 0; r0 < total; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            // owner = first lane whose inclusive sum exceeds r
-            int o = 0;
+        if (fm != 0 && next < T) {
+            const uint32_t r = next + (uint32_t)__popc(fm & lt_mask);
+            const bool take = !active && r < T;
+            const uint32_t rr = r < T ? r : T - 1;
+            int o = 0;   // owner = first lane whose inclusive sum exceeds rr
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t v = __shfl_sync(full, incl, o + step - 1);
-                if (v <= r) o += step;
+                const uint32_t v = __shfl_sync(full, b_incl, o + step - 1);
+                if (v <= rr) o += step;
             }
             o &= 31;
-            const uint32_t e = __shfl_sync(full, excl, o);
-            const P osp = __shfl_sync(full, sp, o);
-            const uint64_t oo = __shfl_sync(full, obase, o);
-            const uint32_t opat = __shfl_sync(full, pat, o);
-            const bool ores = __shfl_sync(full, (int)res, o) != 0;
-            if (r < total) {
-                const uint32_t j = r - e;
-                emit(oo + j, ores ? osp : locate_row<P, NPL, VBITS, ILV>(ix, s_count, (P)(osp + (P)j)), opat);
+            const uint32_t e = __shfl_sync(full, b_incl - b_c, o);
+            const P osp = __shfl_sync(full, b_sp, o);
+            const uint64_t oo = __shfl_sync(full, b_obase, o);
+            const uint32_t opat = __shfl_sync(full, b_pat, o);
+            const bool ores = __shfl_sync(full, (int)b_res, o) != 0;
+            if (take) {
+                const uint32_t j = rr - e;
+                pos = ores ? osp : (P)(osp + (P)j);
+                at = oo + j;
+                pat = opat;
+                res = ores;
+                offset = 0;
+                active = true;
+            }
+            const uint32_t nf = (uint32_t)__popc(fm);
+            next += nf < T - next ? nf : T - next;
+        }
+        if (!__any_sync(full, active)) {
+            if (st == ST_EMPTY && next >= T) break;
+            continue;
+        }
+        // ---- one memory round trip per lane: the sampled SA entry, or one LF step (locate/mod.rs:21-33)
+        // (the SA load is issued before the LF branch and consumed after it, so that both kinds of lanes wait together)
+        {
+            uint64_t quot = 0;
+            const bool direct = ix.fsa != nullptr;   // expanded suffix array: every row is one read
+            const bool sampled = active && !res && (direct || sa_sampled<P>(ix, pos, quot));
+            const bool none = active && !res && !sampled && pos == (P)(ix.sentinel_index - 1);   // None arm, locate/mod.rs:27-30
+            const bool walk = active && !res && !sampled && !none;
+            P value = res ? pos : offset;   // text verification left the text position in sp; None arm: the offset alone
+            if (sampled) value = direct ? fsa_get<P>(ix, pos) : ld_gather<P>(ix.suffix_array + quot);
+            if (walk) {
+                pos = lf_step<P, NPL, VBITS, ILV>(ix, s_count, pos);
+                offset += 1;
+            }
+            if (sampled) value = (P)(value + offset);
+            if (active && !walk) {
+                emit(at, value, pat);
+                active = false;
             }
         }
     }

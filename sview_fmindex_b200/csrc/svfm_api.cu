@@ -116,6 +116,7 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
     if (rc == SVFM_OK) rc = build_ilv_table(ix);
     if (rc == SVFM_OK) rc = build_text_copy(ix);
     if (rc) {
+        if (ix->d_fsa) cudaFree(ix->d_fsa);
         if (ix->d_text) cudaFree(ix->d_text);
         if (ix->d_ilv) cudaFree(ix->d_ilv);
         if (ix->d_ext) cudaFree(ix->d_ext);
@@ -576,12 +577,17 @@ static int build_ext_table(svfm_index* ix) {
     (void)cudaGetLastError();
     return SVFM_OK;
 }
-static std::atomic<uint64_t> g_text{[] {  // build the packed text copy at load (text verification, search_kernels.cuh)
+std::atomic<uint64_t> g_text{[] {  // build the packed text copy at load (text verification, search_kernels.cuh)
     const char* e = std::getenv("SVFM_TEXT");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
+std::atomic<uint64_t> g_full_sa{[] {  // build the expanded suffix array at load (search_kernels.cuh)
+    const char* e = std::getenv("SVFM_FULL_SA");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
+}()};
+// Row-derived structures: the expanded suffix array, then the packed text copy (engine.cuh, run_build_text).
 static int build_text_copy(svfm_index* ix) {
-    if (!g_text.load()) return SVFM_OK;
+    if (!g_text.load() && !g_full_sa.load()) return SVFM_OK;
     const TypeOps* ops = type_ops(ix->type);
     return ops ? ops->build_text(ix->type.planes, ix) : SVFM_ERR_BAD_TYPE;
 }
@@ -1448,6 +1454,7 @@ void svfm_free(svfm_index* ix) {
         delete u;
     }
     ix->up_pool.clear();
+    if (ix->d_fsa) cudaFree(ix->d_fsa);
     if (ix->d_text) cudaFree(ix->d_text);
     if (ix->d_ilv) cudaFree(ix->d_ilv);
     if (ix->d_ext) cudaFree(ix->d_ext);
@@ -1475,12 +1482,13 @@ int svfm_index_info(const svfm_index* ix, svfm_info* out) {
     return SVFM_OK;
 }
 
-int svfm_index_memory(svfm_index* ix, uint64_t out[5]) {
+int svfm_index_memory(svfm_index* ix, uint64_t out[6]) {
     if (!ix || !out) return SVFM_ERR_BAD_ARG;
     out[0] = ix->blob_len;
     out[1] = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
     out[2] = ix->d_ilv ? ix->L.blocks_len * (uint64_t)ix->ilv_stride : 0;
     out[4] = ix->d_text ? ix->text_bytes : 0;
+    out[5] = ix->d_fsa ? ix->fsa_bytes : 0;
     uint64_t scratch = 0;
     std::lock_guard<std::mutex> g(ix->pool_mu);
     for (const svfm_session* s : ix->pool)
@@ -1688,6 +1696,7 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_BUCKET_SORTBACK: g_bucket_sortback.store(value); return SVFM_OK;
         case SVFM_TUNE_SMALL_MAX: g_small_max.store(value); return SVFM_OK;
         case SVFM_TUNE_TEXT: g_text.store(value); return SVFM_OK;
+        case SVFM_TUNE_FULL_SA: g_full_sa.store(value); return SVFM_OK;
         case SVFM_TUNE_L2_PERSIST: g_l2_persist.store(value); return SVFM_OK;
         case SVFM_TUNE_OWN_RADIX: g_own_radix.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;

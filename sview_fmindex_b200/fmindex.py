@@ -213,11 +213,11 @@ class FmIndex:
         return info
 
     def memory(self) -> dict:
-        """Device bytes held by the handle: the blob copy, the two derived structures, idle scratch."""
-        out = (C.c_uint64 * 5)()
+        """Device bytes held by the handle: the blob copy, the derived structures, idle scratch."""
+        out = (C.c_uint64 * 6)()
         _raise(_ffi.lib().svfm_index_memory(self._h, out))
         return {"blob": int(out[0]), "ext_table": int(out[1]), "interleaved_occ": int(out[2]), "scratch": int(out[3]),
-                "text_copy": int(out[4])}
+                "text_copy": int(out[4]), "expanded_sa": int(out[5])}
 
     # ---- single pattern: the reference's API -----------------------------------------------------
     def count(self, pattern) -> int:

@@ -21,21 +21,23 @@ def fm(request):
     copy), at its default thresholds, and without the extended k-mer table (so that long patterns seed from the blob's
     own kLTS), and with the reordered batches radix-sorted back into the caller's order instead of the bucketed sort-back;
     two of the five run without the packed text copy (no text verification), one sorts the sweep items with this library's
-    own radix pass instead of cub: results must not depend on any of it."""
+    own radix pass instead of cub; two run without the expanded suffix array (locate LF-walks to a sampled row as the
+    reference does), three with it: results must not depend on any of it."""
     import sview_fmindex_b200 as fm
     from sview_fmindex_b200 import _ffi
     L = _ffi.lib()
     never = 2**64 - 1
-    sort_min, sweep_min, ext_bits, ilv, bucket, text = {
-        "reorder_always": (0, 0, 24, 1, 1, 1), "reorder_never": (never, never, 24, 0, 1, 0),
-        "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1, 1, 1),
-        "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1, 1, 1), "radix_sortback": (0, 0, 24, 1, 0, 0)}[request.param]
+    sort_min, sweep_min, ext_bits, ilv, bucket, text, full_sa = {
+        "reorder_always": (0, 0, 24, 1, 1, 1, 1), "reorder_never": (never, never, 24, 0, 1, 0, 0),
+        "defaults": (_ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, _ffi.SVFM_TUNE_AUTO, 1, 1, 1, 1),
+        "no_ext_table": (_ffi.SVFM_TUNE_AUTO, 0, 0, 1, 1, 1, 0), "radix_sortback": (0, 0, 24, 1, 0, 0, 1)}[request.param]
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, sort_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_EXT_BITS, ext_bits) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, ilv) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, text) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, full_sa) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 1 if request.param == "radix_sortback" else 0) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
@@ -44,6 +46,7 @@ def fm(request):
     L.svfm_set_tuning(_ffi.SVFM_TUNE_ILV, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, 1)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 0)
 
 
@@ -251,7 +254,7 @@ def test_load_errors(oracle, fm):
     ix = fm.FmIndex.load(blob, ft)
     assert ix.count(b"ACG") == 2
     mem = ix.memory()  # the blob copy byte for byte; derived structures only when enabled
-    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch", "text_copy"}
+    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch", "text_copy", "expanded_sa"}
 
 
 def test_medium_random_batch(oracle, fm):
