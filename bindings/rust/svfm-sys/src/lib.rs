@@ -25,6 +25,7 @@ pub const SVFM_TUNE_TEXT: c_int = 8;
 pub const SVFM_TUNE_L2_PERSIST: c_int = 9;
 pub const SVFM_TUNE_OWN_RADIX: c_int = 10;
 pub const SVFM_TUNE_FULL_SA: c_int = 11;
+pub const SVFM_TUNE_SWEEP_OCC: c_int = 12;
 pub const SVFM_TUNE_AUTO: u64 = 0xffff_ffff_ffff_fffe;
 
 #[repr(C)]
@@ -74,7 +75,7 @@ extern "C" {
                             out: *mut *mut svfm_index, err_detail: *mut u64) -> c_int;
     pub fn svfm_check_blob(blob: *const u8, blob_len: usize, t: svfm_type, out: *mut svfm_info, err_detail: *mut u64) -> c_int;
     pub fn svfm_index_info(ix: *const svfm_index, out: *mut svfm_info) -> c_int;
-    pub fn svfm_index_memory(ix: *mut svfm_index, out: *mut u64) -> c_int; // [6]: blob, ext table, interleaved occ, scratch, text copy, expanded SA
+    pub fn svfm_index_memory(ix: *mut svfm_index, out: *mut u64) -> c_int; // [8]: blob, ext table, interleaved occ, scratch, text copy, expanded SA, sweep occ copy, reserved
     pub fn svfm_locate_batch(ix: *mut svfm_index, pats: *const u8, offs: *const u64, n: u64, fixed_len: u32, flags: u32,
                              out_offs: *mut c_void, positions: *mut c_void, capacity: u64, total: *mut u64) -> c_int;
     // packed fixed-length batches: ceil(len*bits/8) bytes per pattern, symbol indices, first symbol in the lowest bits

@@ -99,8 +99,8 @@ void svfm_free(svfm_index* ix);
 int svfm_index_info(const svfm_index* ix, svfm_info* out);
 /* Device memory held by the handle, in bytes: out[0] the blob copy, out[1] the extended k-mer table, out[2] the
  * interleaved occ copy, out[3] scratch arenas of the idle sessions / upload staging (grow-only until svfm_free),
- * out[4] the packed text copy, out[5] the expanded suffix array. */
-int svfm_index_memory(svfm_index* ix, uint64_t out[6]);
+ * out[4] the packed text copy, out[5] the expanded suffix array, out[6] the sweep occ copy, out[7] reserved (0). */
+int svfm_index_memory(svfm_index* ix, uint64_t out[8]);
 /* Host-only part of load: validate + report sizes without touching a device (LoadError paths). */
 int svfm_check_blob(const uint8_t* blob, size_t blob_len, svfm_type t, svfm_info* out, uint64_t err_detail[2]);
 
@@ -227,10 +227,14 @@ void svfm_host_free(void* p);
  *                      8), derived from the blob at load by walking every row once -- when it takes at most 1/8 of the
  *                      device memory still free.  `locate` then reads one entry per row instead of LF-walking to a sampled
  *                      row (suffix_array/mod.rs:100-105 trades memory for that walk; a B200 has the memory).  1 (default) /
- *                      0 = never (env SVFM_FULL_SA).  Results never depend on it. */
+ *                      0 = never (env SVFM_FULL_SA).  Results never depend on it.
+ * SVFM_TUNE_SWEEP_OCC: indexes loaded from now on with 64-bit vectors, at most three planes and at most four occurring
+ *                      symbols also get the sweep occ copy -- block q's planes and 16-bit checkpoint deltas in ONE 32-byte
+ *                      sector, so that a rank query of the sweep rounds is one 256-bit load (1 default / 0; env
+ *                      SVFM_SWEEP_OCC).  Results never depend on it. */
 enum { SVFM_TUNE_SORT_MIN = 0, SVFM_TUNE_CHUNK = 1, SVFM_TUNE_SWEEP_MIN = 2, SVFM_TUNE_EXT_BITS = 3, SVFM_TUNE_WORKERS = 4,
        SVFM_TUNE_ILV = 5, SVFM_TUNE_BUCKET_SORTBACK = 6, SVFM_TUNE_SMALL_MAX = 7, SVFM_TUNE_TEXT = 8, SVFM_TUNE_L2_PERSIST = 9, SVFM_TUNE_OWN_RADIX = 10,
-       SVFM_TUNE_FULL_SA = 11 };
+       SVFM_TUNE_FULL_SA = 11, SVFM_TUNE_SWEEP_OCC = 12 };
 #define SVFM_TUNE_AUTO 0xfffffffffffffffeull
 int svfm_set_tuning(int key, uint64_t value);
 const char* svfm_last_error(void);    /* thread-local text of the last SVFM_ERR_CUDA */

@@ -41,6 +41,7 @@ SVFM_TUNE_TEXT = 8
 SVFM_TUNE_L2_PERSIST = 9
 SVFM_TUNE_OWN_RADIX = 10
 SVFM_TUNE_FULL_SA = 11
+SVFM_TUNE_SWEEP_OCC = 12
 SVFM_TUNE_AUTO = 0xFFFFFFFFFFFFFFFE
 SVFM_REVERSED = 1
 SVFM_SORTED = 2

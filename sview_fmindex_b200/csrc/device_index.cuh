@@ -57,6 +57,9 @@ struct DevIndex {
     // of EVERY SA row, 32-bit entries when the text is shorter than 2^32 symbols (fsa32), else P; NULL = not built
     const void* fsa;
     uint32_t fsa32;
+    // compact occ copy for the sweep rounds, derived from the blob at load (search_kernels.cuh, "sweep occ copy"): one
+    // 32-byte sector per block = its planes + 16-bit checkpoint deltas of the occurring symbols; NULL = not built
+    const uint8_t* swp;
 };
 
 // the symbol maps alone (kernels that do not touch the index arrays)

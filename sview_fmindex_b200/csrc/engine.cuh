@@ -47,6 +47,7 @@ struct svfm_index {
     void* d_fsa = nullptr;         // expanded suffix array (text position of every SA row), or NULL
     uint32_t fsa32 = 0;            // its entries are 32 bits wide
     uint64_t fsa_bytes = 0;
+    uint8_t* d_swp = nullptr;      // sweep occ copy (blocks_len entries of 32 bytes), or NULL
     std::mutex pool_mu;
     std::vector<svfm_session*> pool;  // idle sessions for the host-buffer entry points
     std::vector<svfm_uploader*> up_pool;  // idle uploaders
@@ -128,6 +129,7 @@ static DevIndex<P> make_dev_index(const svfm_index* ix) {
     d.text_bits = ix->text_bits;
     d.fsa = ix->d_fsa;
     d.fsa32 = ix->fsa32;
+    d.swp = ix->d_swp;
     return d;
 }
 
@@ -501,7 +503,24 @@ static int run_search_sweep_r(svfm_session* s, const PatternBatch& pb, const Sor
             SVFM_CUDA(cudaGetLastError());
             return SVFM_OK;
         };
-        if (r == 0) {
+        constexpr bool SWP_OK = VBITS == 64 && NPL <= 3;   // the sweep occ copy exists for these block shapes only
+        bool launched = false;
+        if constexpr (SWP_OK) {
+            if (dix.swp) {
+                launched = true;
+                if (r == 0) {
+                    if (part == PART_SYMBOLS) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_SYMBOLS, true>);
+                    else if (part == PART_INDEX) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_INDEX, true>);
+                    else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_NONE, true>);
+                } else {
+                    if (part == PART_SYMBOLS) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_SYMBOLS, true>);
+                    else if (part == PART_INDEX) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_INDEX, true>);
+                    else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, false, PART_NONE, true>);
+                }
+            }
+        }
+        if (launched) {
+        } else if (r == 0) {
             if (part == PART_SYMBOLS) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_SYMBOLS>);
             else if (part == PART_INDEX) rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_INDEX>);
             else rc = launch(sweep_round_kernel<P, NPL, VBITS, R, true, PART_NONE>);
@@ -570,7 +589,17 @@ static int run_locate(svfm_session* s, uint64_t n, const uint32_t* idx, const vo
         heavy.pat = (uint32_t*)s->heavy_pat.ptr;
         heavy.capacity = heavy_seen;
     }
-    {
+    if (dix.fsa) {   // expanded suffix array: one read per row, no walk (search_kernels.cuh, locate_direct_kernel)
+        PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
+        auto launch = [&](auto kernel) {
+            const int grid = resident_grid(kernel, (n + LOCATE_DIRECT_ITEMS - 1) / LOCATE_DIRECT_ITEMS, LOCATE_THREADS, s->ix->device);
+            kernel<<<grid, LOCATE_THREADS, 0, s->stream>>>(dix, idx, (const P*)d_sp_work, (const P*)d_cnt_work, d_offs, n,
+                                                           (P*)d_positions, d_rec_key, heavy, bk, d_resolved);
+        };
+        if (bucket) launch(locate_direct_kernel<P, true>);
+        else launch(locate_direct_kernel<P, false>);
+        SVFM_CUDA(cudaGetLastError());
+    } else {
         PhaseTimer pt(s, SVFM_PHASE_LOCATE, 1);
         auto launch = [&](auto kernel) {
             const int grid = resident_grid(kernel, n, LOCATE_THREADS, s->ix->device);

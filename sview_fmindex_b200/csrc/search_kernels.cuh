@@ -107,6 +107,76 @@ __device__ __forceinline__ void backward_step(const DevIndex<P>& ix, uint32_t sy
     SVFM_ASSERT(sp <= ep);   // ranks are monotone (with_slice.rs:27: the loop condition relies on it)
 }
 
+// ---- sweep occ copy -------------------------------------------------------------------------------------------------------
+// The sweep rounds are bound by the number of L1 requests and sectors they touch, not by DRAM (ncu, round 0 of a 10^8-pattern
+// batch: l1tex throughput 86 %, 14 sector lookups per item -- a rank query on the blob is a checkpoint word plus three plane
+// words from two arrays, for each end of the interval).  For indexes with 64-bit vectors, at most three planes and at most
+// four occurring symbols (DNA) the engine keeps a third form of the occ data: entry q = ONE 32-byte sector holding the planes
+// of block q (words 0 .. NPL-1) and, in word NPL, the checkpoint counts of the occurring symbols as 16-bit deltas against
+// the checkpoint row of the block's SUPERBLOCK (SWP_SUPER consecutive blocks; that row is read from the blob in place --
+// one row per 32 768 text positions, a few hundred KB in all, resident in L1/L2).  A rank query is then one 256-bit load.
+// Derived from the blob, bytes only: rank = superblock row + delta + popcount, the same sum bwm/mod.rs:197-215 forms.
+constexpr uint32_t SWP_SUPER_SHIFT = 9;                       // 512 blocks of 64 positions: deltas stay below 2^15
+constexpr uint32_t SWP_SUPER_MASK = (1u << SWP_SUPER_SHIFT) - 1u;
+struct SwpEntry { unsigned long long w[4]; };
+__device__ __forceinline__ SwpEntry swp_load(const uint8_t* entry) {
+    SwpEntry e;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e.w[0]), "=l"(e.w[1]), "=l"(e.w[2]), "=l"(e.w[3]) : "l"(entry));
+    return e;
+}
+struct SwpSyms { uint8_t present[4]; uint32_t s_eff; };
+template <class P>
+__global__ void __launch_bounds__(256)
+swp_build_kernel(const unsigned long long* __restrict__ blocks, uint32_t npl, const P* __restrict__ ck, uint32_t S, SwpSyms syms,
+                 uint64_t blocks_len, ulonglong4* __restrict__ out) {
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < blocks_len; q += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long w[4] = {0, 0, 0, 0};
+        for (uint32_t v = 0; v < npl; v++) w[v] = blocks[q * npl + v];
+        const uint64_t sup = q & ~(uint64_t)SWP_SUPER_MASK;
+        unsigned long long d = 0;
+        for (uint32_t j = 0; j < syms.s_eff; j++) {
+            const uint64_t delta = (uint64_t)(ck[q * S + syms.present[j]] - ck[sup * S + syms.present[j]]);
+            SVFM_ASSERT(delta < 65536);
+            d |= delta << (16 * j);
+        }
+        w[npl] = d;
+        out[q] = make_ulonglong4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// backward_step on the sweep occ copy: `code` = rank of the symbol among the occurring ones, sym = its symbol index.
+template <class P, int NPL>
+__device__ __forceinline__ void backward_step_swp(const DevIndex<P>& ix, uint32_t code, uint32_t sym, P c, P& sp, P& ep) {
+    using B = Block<NPL, 64>;
+    using Q = typename QuotientOf<P>::type;
+    Q q0, q1;
+    uint32_t r0, r1;
+    rank_addr<P, 64>(ix, sp, q0, r0);
+    rank_addr<P, 64>(ix, ep, q1, r1);
+    const SwpEntry e0 = swp_load(ix.swp + (uint64_t)q0 * 32);
+    const P sup0 = ld_gather<P>(ix.rank_checkpoints + ((uint64_t)(q0 & ~(Q)SWP_SUPER_MASK) * ix.symbol_count + sym));
+    const bool two = q1 != q0;
+    const bool two_sup = ((q0 ^ q1) >> SWP_SUPER_SHIFT) != 0;
+    SwpEntry e1;
+    e1.w[0] = e1.w[1] = e1.w[2] = e1.w[3] = 0;
+    P sup1 = 0;
+    if (two) e1 = swp_load(ix.swp + (uint64_t)q1 * 32);
+    if (two_sup) sup1 = ld_gather<P>(ix.rank_checkpoints + ((uint64_t)(q1 & ~(Q)SWP_SUPER_MASK) * ix.symbol_count + sym));
+    unsigned long long flip[NPL];
+#pragma unroll
+    for (int v = 0; v < NPL; v++) flip[v] = ((sym >> v) & 1u) ? 0ull : ~0ull;
+    unsigned long long m0 = e0.w[0] ^ flip[0], m1 = e1.w[0] ^ flip[0];
+#pragma unroll
+    for (int v = 1; v < NPL; v++) { m0 &= e0.w[v] ^ flip[v]; m1 &= e1.w[v] ^ flip[v]; }
+    const uint32_t sh = 16u * code;
+    const uint32_t d0 = (uint32_t)(e0.w[NPL] >> sh) & 0xffffu, d1 = (uint32_t)(e1.w[NPL] >> sh) & 0xffffu;
+    sp = (P)(c + sup0 + (P)d0 + (P)popc_top((uint64_t)m0, r0));
+    m1 = two ? m1 : m0;
+    ep = (P)(c + (two_sup ? sup1 : sup0) + (P)(two ? d1 : d0) + (P)popc_top((uint64_t)m1, r1));
+    SVFM_ASSERT(sp <= ep);
+    (void)sizeof(B);
+}
+
 // Locality key of a pattern = its trailing symbols packed `bits` per symbol from the top of a u64, the
 // LAST symbol most significant (backward search consumes the pattern from its end, so patterns that share
 // a suffix walk the same checkpoint rows and blocks for as many steps as the shared suffix is long).
@@ -998,7 +1068,7 @@ struct SweepRoundIO {
 //   matter (scatter_counts_kernel places by index), so a tile reserves its space with one atomic add per digit.
 // Tiles are handed out by an atomic counter, so a tile's predecessors are always running or done.
 // PART_NONE: items are written back in place.
-template <class P, int NPL, int VBITS, class R, bool FIRST, int PART>
+template <class P, int NPL, int VBITS, class R, bool FIRST, int PART, bool SWP = false>
 __global__ void __launch_bounds__(ROUND_THREADS, SVFM_ROUND_MIN_CTAS)
 sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shift, uint32_t steps, uint32_t nbins,
                    const SweepRoundIO<P, R> io) {
@@ -1176,8 +1246,10 @@ sweep_round_kernel(const DevIndex<P> ix, uint64_t n, uint32_t bits, uint32_t shi
                 P ep = (P)(sp[k] + cnt[k]);
                 R left = (R)(rest[k] >> shift);
                 for (uint32_t t = 0; t < steps && sp[k] < ep; t++, left >>= bits) {
-                    const uint32_t sy = s_present[(uint32_t)(left & sym_mask)];
-                    backward_step<P, NPL, VBITS>(ix, sy, s_count[sy], sp[k], ep);
+                    const uint32_t code = (uint32_t)(left & sym_mask);
+                    const uint32_t sy = s_present[code];
+                    if constexpr (SWP) backward_step_swp<P, NPL>(ix, code, sy, s_count[sy], sp[k], ep);
+                    else backward_step<P, NPL, VBITS>(ix, sy, s_count[sy], sp[k], ep);
                 }
                 cnt[k] = (P)(ep - sp[k]);
             }
@@ -1560,6 +1632,88 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
             if (active && !walk) {
                 emit(at, value, pat);
                 active = false;
+            }
+        }
+    }
+}
+
+// Locate with the expanded suffix array: every row is ONE read, so there is nothing to balance between lanes -- a thread
+// takes LOCATE_DIRECT_ITEMS work items (consecutive threads take consecutive items: coalesced loads of sp / cnt / idx, and
+// in SA order -- the sweep search's last partition -- neighbouring lanes read neighbouring array entries), reserves each
+// item's output slots, and copies its rows' entries.  Items with more than 32 rows are spread over the warp, more than
+// HEAVY_ROWS go to the heavy list as in locate_warp_kernel.  Same outputs as locate_warp_kernel.
+constexpr int LOCATE_DIRECT_ITEMS = 4;
+template <class P, bool BUCKET>
+__global__ void __launch_bounds__(LOCATE_THREADS)
+locate_direct_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
+                     const P* __restrict__ cnt_work, const uint64_t* __restrict__ offs, uint64_t n,
+                     P* __restrict__ positions, uint32_t* __restrict__ rec_key, HeavyList<P> heavy, BucketOut<P> bk,
+                     const uint8_t* __restrict__ resolved) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    auto emit = [&](uint64_t at, P pos, uint32_t pattern) {
+        if constexpr (BUCKET) {
+            SbRec<P> r;
+            r.pos = pos;
+            r.idx = pattern;
+            if constexpr (sizeof(P) == 8) r.pad = 0;
+            bk.recs[at] = r;
+        } else {
+            positions[at] = pos;
+            if (rec_key) rec_key[at] = pattern;
+        }
+    };
+    const uint64_t per_cta = (uint64_t)LOCATE_THREADS * LOCATE_DIRECT_ITEMS;
+    const uint64_t n_tiles = (n + per_cta - 1) / per_cta;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {   // whole tiles: every lane of a warp stays in the loop
+        P sp[LOCATE_DIRECT_ITEMS], cw[LOCATE_DIRECT_ITEMS];
+        uint32_t pat[LOCATE_DIRECT_ITEMS];
+        bool res[LOCATE_DIRECT_ITEMS];
+        uint64_t obase[LOCATE_DIRECT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < LOCATE_DIRECT_ITEMS; k++) {
+            const uint64_t w = tile * per_cta + (uint64_t)k * LOCATE_THREADS + threadIdx.x;
+            cw[k] = 0; sp[k] = 0; pat[k] = (uint32_t)w; res[k] = false;
+            if (w < n) {
+                cw[k] = cnt_work[w];
+                sp[k] = sp_work[w];
+                if (idx) pat[k] = idx[w];
+                if (resolved) res[k] = resolved[w] != 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LOCATE_DIRECT_ITEMS; k++) {
+            obase[k] = 0;
+            if (cw[k] != 0) {
+                if constexpr (BUCKET) obase[k] = atomicAdd(bk.cursor + (pat[k] >> SB_SHIFT), (unsigned long long)cw[k]);
+                else obase[k] = offs[tile * per_cta + (uint64_t)k * LOCATE_THREADS + threadIdx.x];
+                if ((uint64_t)cw[k] > HEAVY_ROWS) {
+                    const unsigned long long h = atomicAdd(heavy.n, 1ull);
+                    if (h < heavy.capacity) { heavy.sp[h] = sp[k]; heavy.cnt[h] = cw[k]; heavy.obase[h] = obase[k]; heavy.pat[h] = pat[k]; }
+                    cw[k] = 0;
+                }
+            }
+        }
+        // the first row of every item: all reads in flight before the first store
+        P first[LOCATE_DIRECT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < LOCATE_DIRECT_ITEMS; k++) first[k] = (cw[k] != 0 && !res[k]) ? fsa_get<P>(ix, sp[k]) : sp[k];
+#pragma unroll
+        for (int k = 0; k < LOCATE_DIRECT_ITEMS; k++) {
+            if (cw[k] != 0) emit(obase[k], first[k], pat[k]);
+            // further rows: up to 32 by the owner, more by the whole warp
+            const bool wide = (uint64_t)cw[k] > 32;
+            if (cw[k] > 1 && !wide)
+                for (uint32_t j = 1; j < (uint32_t)cw[k]; j++) emit(obase[k] + j, fsa_get<P>(ix, (P)(sp[k] + (P)j)), pat[k]);
+            unsigned wm = __ballot_sync(full, wide);
+            while (wm) {
+                const int o = __ffs(wm) - 1;
+                wm &= wm - 1;
+                const uint32_t oc = (uint32_t)__shfl_sync(full, (uint32_t)cw[k], o);   // <= HEAVY_ROWS
+                const P osp = __shfl_sync(full, sp[k], o);
+                const uint64_t oo = __shfl_sync(full, obase[k], o);
+                const uint32_t opat = __shfl_sync(full, pat[k], o);
+                for (uint32_t j = 1 + lane; j < oc; j += 32) emit(oo + j, fsa_get<P>(ix, (P)(osp + (P)j)), opat);
             }
         }
     }

@@ -69,6 +69,7 @@ static int finish_load(svfm_index* ix) {
 static int build_ext_table(svfm_index* ix);
 static int build_ilv_table(svfm_index* ix);
 static int build_text_copy(svfm_index* ix);
+static int build_swp_table(svfm_index* ix);
 
 static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int device, bool src_on_device,
                        svfm_index** out, uint64_t err_detail[2]) {
@@ -114,8 +115,10 @@ static int load_common(const uint8_t* blob, size_t blob_len, svfm_type t, int de
     rc = finish_load(ix);
     if (rc == SVFM_OK) rc = build_ext_table(ix);
     if (rc == SVFM_OK) rc = build_ilv_table(ix);
+    if (rc == SVFM_OK) rc = build_swp_table(ix);
     if (rc == SVFM_OK) rc = build_text_copy(ix);
     if (rc) {
+        if (ix->d_swp) cudaFree(ix->d_swp);
         if (ix->d_fsa) cudaFree(ix->d_fsa);
         if (ix->d_text) cudaFree(ix->d_text);
         if (ix->d_ilv) cudaFree(ix->d_ilv);
@@ -217,11 +220,16 @@ static std::atomic<uint64_t> g_sweep_min{[] {
     const char* e = std::getenv("SVFM_SWEEP_MIN");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
-// AUTO: the measured break-even with the plain search kernel on a 1 Gbp index -- about 5.5 M patterns with a 2^24-entry
-// extended table (8 steps left of a 20-mer), about 10 M with a 2^28-entry one (6 steps left).
-static uint64_t sweep_min_patterns(const svfm_index* ix) {
+// AUTO: the measured break-even with the plain search kernel on a 1 Gbp index (B200, 20-mers).  Without the row-derived
+// structures: about 5.5 M patterns with a 2^24-entry extended table (8 steps left of a 20-mer), about 10 M with a 2^28-entry
+// one (6 steps left).  With the packed text copy AND the expanded suffix array the plain kernel finishes a pattern with one
+// array read and one text comparison as soon as a single row is left, and `locate` costs it one more read: count+locate
+// 4.2 / 8.3 / 16.7 / 33 M patterns: 0.69 / 1.31 / 2.55 / 4.99 ms against 1.27 / 1.70 / 2.88 / 4.30 ms for the sweep search
+// (break-even ~24 M); count alone 7.3-7.5 G patterns/s against 5.8 / 7.4 / 9.1 / 10.5 (break-even ~8 M).
+static uint64_t sweep_min_patterns(const svfm_index* ix, bool for_locate = true) {
     const uint64_t v = g_sweep_min.load();
     if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
+    if (ix->d_text && ix->d_fsa) return for_locate ? (uint64_t)(24u << 20) : (uint64_t)(8u << 20);
     return ix->ext_entries >= (1ull << 26) ? (uint64_t)(10u << 20) : (uint64_t)(5u << 20);
 }
 static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
@@ -255,7 +263,7 @@ static std::atomic<uint64_t> g_sweep_final_sort{[] {  // locate: partition once 
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
 }()};
 
-static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& pb) {
+static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& pb, bool for_locate) {
     SortPlan p;
     const uint32_t S = ix->L.symbol_count;
     p.bits = (uint32_t)bits_for(S);
@@ -265,7 +273,7 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
     // with any other symbol has count 0 before the search starts), ceil(log2 s_eff) bits each
     uint32_t rank_bits = (uint32_t)bits_for(ix->symbols_present);
     if (rank_bits == 0) rank_bits = 1;
-    if (!pb.offs && ix->ext_m && n >= sweep_min_patterns(ix) && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
+    if (!pb.offs && ix->ext_m && n >= sweep_min_patterns(ix, for_locate) && n < (1ull << 30) /* look-back descriptors: 30-bit counts */ &&
         pb.fixed_len >= ix->ext_m && (uint64_t)(pb.fixed_len - ix->ext_m) * rank_bits <= 64) {
         p.sweep = true;
         p.bits = rank_bits;
@@ -284,7 +292,7 @@ static SortPlan plan_sort(const svfm_index* ix, uint64_t n, const PatternBatch& 
         // 2 rounds), the generic kernel beyond (32-mers on 3.1 Gbp: 6 rounds, 12-mer proteins: 6 rounds of one step).
         static const uint32_t max_rounds_env = [] { const char* e = std::getenv("SVFM_SWEEP_MAX_ROUNDS"); return e ? (uint32_t)atoi(e) : 2u; }();
         const uint32_t rounds = (pb.fixed_len - ix->ext_m + p.steps_per_round - 1) / p.steps_per_round;
-        if (ix->d_text && sweep_min_patterns(ix) != 0 && rounds > max_rounds_env) { p.sweep = false; p.bits = (uint32_t)bits_for(S) ? (uint32_t)bits_for(S) : 1u; }
+        if (ix->d_text && sweep_min_patterns(ix, for_locate) != 0 && rounds > max_rounds_env) { p.sweep = false; p.bits = (uint32_t)bits_for(S) ? (uint32_t)bits_for(S) : 1u; }
         else return p;
     }
     if (n < sort_min_patterns(ix)) return p;
@@ -548,6 +556,37 @@ static int build_ilv_table(svfm_index* ix) {
     ix->ilv_ck_off = (uint32_t)ck_off;
     return SVFM_OK;
 }
+// Sweep occ copy: one 32-byte sector per block (search_kernels.cuh).  Derived from the blob, bytes only; optional.
+static std::atomic<uint64_t> g_sweep_occ{[] {
+    const char* e = std::getenv("SVFM_SWEEP_OCC");
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)1;
+}()};
+static int build_swp_table(svfm_index* ix) {
+    if (!g_sweep_occ.load()) return SVFM_OK;
+    const Layout& L = ix->L;
+    const uint32_t npl = ix->type.planes, s_eff = ix->symbols_present;
+    if (ix->type.vec_bits != 64 || npl > 3 || s_eff < 1 || s_eff > 4) return SVFM_OK;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || L.blocks_len * 32 > free_b / 8) { (void)cudaGetLastError(); return SVFM_OK; }
+    void* d = nullptr;
+    if (cudaMalloc(&d, L.blocks_len * 32) != cudaSuccess) { (void)cudaGetLastError(); return SVFM_OK; }
+    SwpSyms syms{};
+    syms.s_eff = s_eff;
+    for (uint32_t j = 0; j < s_eff; j++) syms.present[j] = ix->present[j];
+    const int grid = grid_for(L.blocks_len, 256, ix->device);
+    const unsigned long long* blocks = reinterpret_cast<const unsigned long long*>(ix->d_blob + L.off_blocks);
+    if (ix->type.pos_bits == 32)
+        swp_build_kernel<uint32_t><<<grid, 256>>>(blocks, npl, reinterpret_cast<const uint32_t*>(ix->d_blob + L.off_rank_checkpoints),
+                                                  L.bwm_symbol_count, syms, L.blocks_len, (ulonglong4*)d);
+    else
+        swp_build_kernel<uint64_t><<<grid, 256>>>(blocks, npl, reinterpret_cast<const uint64_t*>(ix->d_blob + L.off_rank_checkpoints),
+                                                  L.bwm_symbol_count, syms, L.blocks_len, (ulonglong4*)d);
+    g_launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d); SVFM_CUDA(e); }
+    ix->d_swp = (uint8_t*)d;
+    return SVFM_OK;
+}
 static std::atomic<uint64_t> g_l2_persist{[] {  // extended tables up to this many bytes get an L2 persisting window (0 = never)
     const char* e = std::getenv("SVFM_L2_PERSIST");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)(64u << 20);
@@ -644,7 +683,7 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
     SVFM_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), s->stream));
     SVFM_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), s->stream));
     if (pb.n == 0) return SVFM_OK;
-    const SortPlan plan = plan_sort(s->ix, pb.n, pb);
+    const SortPlan plan = plan_sort(s->ix, pb.n, pb, false);
     if (!plan.sorted && !plan.sweep) return dispatch_search(s, pb, nullptr, nullptr, 1, nullptr, d_counts_out);
     const uint64_t P = s->ix->type.pos_bits / 8;
     const uint64_t* keys = nullptr;
@@ -680,7 +719,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     const uint64_t rn = rsv(s, pb.n);
     if ((rc = s->sp.reserve((rn + 1) * P))) return rc;
     if ((rc = s->cnt.reserve((rn + 1) * P))) return rc;
-    const SortPlan plan = plan_sort(s->ix, pb.n, pb);
+    const SortPlan plan = plan_sort(s->ix, pb.n, pb, true);
     const uint64_t* keys = nullptr;
     const uint32_t* idx = nullptr;
     const bool offs32 = (flags & SVFM_OFFS32) != 0;
@@ -862,15 +901,17 @@ struct ChunkPlan {
 // aligned for the TMA staging).  The LAST chunk is halved repeatedly (down to ~1 Mi patterns): the upload stream is the
 // bottleneck of a host batch, so what remains after the last byte has arrived -- kernels + download of the final
 // chunk -- should be small.
-// AUTO: 8 Mi patterns when the upload is what bounds the call (byte patterns: 20 B each at PCIe speed), 16 Mi when the
-// patterns arrive packed (<= 8 B each): the chunks are then large enough for the sweep search, and the device pipeline, not
-// the bus, is the bottleneck (measured on 10^8 20-mers: packed 2.68 / 3.45 / 2.62 G patterns/s with 8 / 16 / 32 Mi chunks,
-// byte patterns 2.24 / 2.10 / 2.03).
+// AUTO: 8 Mi patterns.  Measured on B200, 10^8 20-mers, count+locate, pinned buffers (end-to-end G patterns/s): byte patterns
+// 2.45 / 2.41 / 2.36 / 2.17 with 4 / 8 / 12 / 32 Mi chunks (the upload bounds the call: 2 GB at PCIe speed); 2-bit packed
+// patterns 4.39 / 4.46 / 4.33 / 3.89 / 3.65 / 3.31 with 4 / 6 / 8 / 12 / 16 / 32 Mi chunks -- chunks this size take the plain
+// search kernel (see sweep_min_patterns), whose time per pattern does not depend on the batch size, and small chunks keep
+// the head (first upload + first kernels) and the tail (last download) of the pipeline short.
 static ChunkPlan plan_chunks(uint64_t n, uint64_t bytes_per_pattern = 0) {
     ChunkPlan p;
     p.n = n;
     uint64_t c = g_chunk_patterns.load();
-    if (c == (uint64_t)SVFM_TUNE_AUTO) c = (bytes_per_pattern && bytes_per_pattern <= 8) ? (16u << 20) : (8u << 20);
+    if (c == (uint64_t)SVFM_TUNE_AUTO) c = 8u << 20;
+    (void)bytes_per_pattern;
     if (c == 0) c = n;
     uint64_t k = (n + c - 1) / c;
     if (k == 0) k = 1;
@@ -1454,6 +1495,7 @@ void svfm_free(svfm_index* ix) {
         delete u;
     }
     ix->up_pool.clear();
+    if (ix->d_swp) cudaFree(ix->d_swp);
     if (ix->d_fsa) cudaFree(ix->d_fsa);
     if (ix->d_text) cudaFree(ix->d_text);
     if (ix->d_ilv) cudaFree(ix->d_ilv);
@@ -1482,13 +1524,15 @@ int svfm_index_info(const svfm_index* ix, svfm_info* out) {
     return SVFM_OK;
 }
 
-int svfm_index_memory(svfm_index* ix, uint64_t out[6]) {
+int svfm_index_memory(svfm_index* ix, uint64_t out[8]) {
     if (!ix || !out) return SVFM_ERR_BAD_ARG;
     out[0] = ix->blob_len;
     out[1] = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
     out[2] = ix->d_ilv ? ix->L.blocks_len * (uint64_t)ix->ilv_stride : 0;
     out[4] = ix->d_text ? ix->text_bytes : 0;
     out[5] = ix->d_fsa ? ix->fsa_bytes : 0;
+    out[6] = ix->d_swp ? ix->L.blocks_len * 32 : 0;
+    out[7] = 0;
     uint64_t scratch = 0;
     std::lock_guard<std::mutex> g(ix->pool_mu);
     for (const svfm_session* s : ix->pool)
@@ -1697,6 +1741,7 @@ int svfm_set_tuning(int key, uint64_t value) {
         case SVFM_TUNE_SMALL_MAX: g_small_max.store(value); return SVFM_OK;
         case SVFM_TUNE_TEXT: g_text.store(value); return SVFM_OK;
         case SVFM_TUNE_FULL_SA: g_full_sa.store(value); return SVFM_OK;
+        case SVFM_TUNE_SWEEP_OCC: g_sweep_occ.store(value); return SVFM_OK;
         case SVFM_TUNE_L2_PERSIST: g_l2_persist.store(value); return SVFM_OK;
         case SVFM_TUNE_OWN_RADIX: g_own_radix.store(value); return SVFM_OK;
         default: return SVFM_ERR_BAD_ARG;

@@ -214,10 +214,10 @@ class FmIndex:
 
     def memory(self) -> dict:
         """Device bytes held by the handle: the blob copy, the derived structures, idle scratch."""
-        out = (C.c_uint64 * 6)()
+        out = (C.c_uint64 * 8)()
         _raise(_ffi.lib().svfm_index_memory(self._h, out))
         return {"blob": int(out[0]), "ext_table": int(out[1]), "interleaved_occ": int(out[2]), "scratch": int(out[3]),
-                "text_copy": int(out[4]), "expanded_sa": int(out[5])}
+                "text_copy": int(out[4]), "expanded_sa": int(out[5]), "sweep_occ": int(out[6])}
 
     # ---- single pattern: the reference's API -----------------------------------------------------
     def count(self, pattern) -> int:

@@ -38,6 +38,7 @@ def fm(request):
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, text) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, full_sa) == 0
+    assert L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_OCC, 0 if request.param == "radix_sortback" else 1) == 0
     assert L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 1 if request.param == "radix_sortback" else 0) == 0
     yield fm
     L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, _ffi.SVFM_TUNE_AUTO)
@@ -47,6 +48,7 @@ def fm(request):
     L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_TEXT, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, 1)
+    L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_OCC, 1)
     L.svfm_set_tuning(_ffi.SVFM_TUNE_OWN_RADIX, 0)
 
 
@@ -254,7 +256,7 @@ def test_load_errors(oracle, fm):
     ix = fm.FmIndex.load(blob, ft)
     assert ix.count(b"ACG") == 2
     mem = ix.memory()  # the blob copy byte for byte; derived structures only when enabled
-    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch", "text_copy", "expanded_sa"}
+    assert mem["blob"] == blob.size and set(mem) == {"blob", "ext_table", "interleaved_occ", "scratch", "text_copy", "expanded_sa", "sweep_occ"}
 
 
 def test_medium_random_batch(oracle, fm):
