@@ -189,12 +189,12 @@ void svfm_host_free(void* p);
  *                      UINT64_MAX = never; default SVFM_TUNE_AUTO = never when the index has an extended k-mer table
  *                      -- nothing is left to share after the lookup -- else 131072; env SVFM_SORT_MIN).
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
- *                      pipeline upload / kernels / download (0 = one chunk; default SVFM_TUNE_AUTO = 8 Mi, 16 Mi for
- *                      packed patterns of at most 8 bytes; env SVFM_CHUNK).
+ *                      pipeline upload / kernels / download (0 = one chunk; default SVFM_TUNE_AUTO = 8 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
  *                      kept sorted by SA position and moves through the index as streams (default SVFM_TUNE_AUTO = the
- *                      measured break-even with the plain search kernel on a 1 Gbp index: 5 Mi patterns with a 2^24-entry
- *                      extended table, 10 Mi with a 2^28-entry one; env SVFM_SWEEP_MIN).
+ *                      measured break-even with the plain search kernel on a 1 Gbp index: 24 Mi patterns for locate and
+ *                      8 Mi for count when the index has its packed text copy and expanded suffix array, else 5 Mi
+ *                      with a 2^24-entry extended table and 10 Mi with a 2^28-entry one; env SVFM_SWEEP_MIN).
  * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries (and at most
  *                      text_len / 2), derived from the blob at load (0 = none; default SVFM_TUNE_AUTO = 28, i.e. 2 GiB
  *                      for u32 positions, when that is under 1/16 of the free device memory, else 24 = 128 MiB; env

@@ -1642,7 +1642,10 @@ locate_warp_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const
 // in SA order -- the sweep search's last partition -- neighbouring lanes read neighbouring array entries), reserves each
 // item's output slots, and copies its rows' entries.  Items with more than 32 rows are spread over the warp, more than
 // HEAVY_ROWS go to the heavy list as in locate_warp_kernel.  Same outputs as locate_warp_kernel.
-constexpr int LOCATE_DIRECT_ITEMS = 4;
+#ifndef SVFM_LOCATE_DIRECT_ITEMS
+#define SVFM_LOCATE_DIRECT_ITEMS 4
+#endif
+constexpr int LOCATE_DIRECT_ITEMS = SVFM_LOCATE_DIRECT_ITEMS;
 template <class P, bool BUCKET>
 __global__ void __launch_bounds__(LOCATE_THREADS)
 locate_direct_kernel(const DevIndex<P> ix, const uint32_t* __restrict__ idx, const P* __restrict__ sp_work,
@@ -1809,7 +1812,13 @@ sb_scan_kernel(const uint32_t* __restrict__ hist, uint64_t nb, uint64_t* __restr
 // A bucket must hold fewer than 2^32 records (the host falls back to the radix sort-back above 2^32 in total).
 constexpr int SB_PLACE_THREADS = 256;
 constexpr uint32_t SB_PAD = SB_BUCKET + SB_BUCKET / 32;
-constexpr uint32_t SB_STAGE = SB_BUCKET + SB_BUCKET / 2;   // records staged in shared memory (6144; a bucket averages occ x 4096)
+// Staging the placed positions in shared memory (coalesced stores) was measured SLOWER than storing them straight into the
+// bucket's 16 KB output window, which L2 merges into full lines: the staging buffer cut the occupancy from 6 to 3 CTAs per
+// SM (0.99 against 0.84 ms per 10^8 records).  SVFM_SB_STAGE > 0 brings it back for buckets of up to that many records.
+#ifndef SVFM_SB_STAGE
+#define SVFM_SB_STAGE 0
+#endif
+constexpr uint32_t SB_STAGE = SVFM_SB_STAGE;
 constexpr size_t SB_PLACE_SMEM = (2 * (size_t)SB_PAD) * 4;  // + SB_STAGE * sizeof(P)
 __device__ __forceinline__ uint32_t sb_pad(uint32_t k) { return k + (k >> 5); }
 template <class P>

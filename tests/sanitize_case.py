@@ -8,7 +8,7 @@ kernel of the hot path on a small index, results checked against the CPU oracle.
 Covers: GPU index builder, extended-table / interleaved-copy / text-copy construction, pack_sweep_kernel (TMA bulk copies +
 mbarriers), sweep_round_kernel in all three partition modes (look-back descriptors, atomic reservation), locate in bucket and
 CSR mode (incl. the heavy list), sb_scan / sb_place, scatter_counts, the generic search kernel with text verification, the
-small-batch kernel, packed input, the radix sort-back."""
+small-batch kernel, packed input, the radix sort-back; with and without the expanded suffix array and the sweep occ copy."""
 import os
 import sys
 
@@ -45,7 +45,9 @@ for (p, planes, v, k, r) in ((32, 3, 64, 3, 2), (64, 2, 128, 2, 3)):
     blob = fm.aligned_empty(b.blob_size())
     b.build(text, blob)                                                    # GPU builder
     ora = po.OracleFmIndex.load(blob, po.IndexType(p, planes, v, True))
-    for sweep_min, bucket, ext_bits in ((0, 1, 16), (0, 0, 12), (2**64 - 1, 1, 16)):
+    for sweep_min, bucket, ext_bits, derived in ((0, 1, 16, 1), (0, 0, 12, 0), (2**64 - 1, 1, 16, 1), (2**64 - 1, 1, 16, 0)):
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, derived)       # 0: locate LF-walks (locate_warp_kernel), 1: locate_direct_kernel
+        L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_OCC, derived)     # sweep rounds on the 32-byte occ copy / on the blob in place
         L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_MIN, sweep_min)
         L.svfm_set_tuning(_ffi.SVFM_TUNE_SORT_MIN, 0 if sweep_min == 0 else 2**64 - 1)
         L.svfm_set_tuning(_ffi.SVFM_TUNE_BUCKET_SORTBACK, bucket)
@@ -69,4 +71,6 @@ for (p, planes, v, k, r) in ((32, 3, 64, 3, 2), (64, 2, 128, 2, 3)):
         o4, p4 = gpu.locate_batch(pats[:2000])
         assert np.array_equal(o3.astype(np.uint64), o4) and np.array_equal(p3, p4)
         gpu.close()
+L.svfm_set_tuning(_ffi.SVFM_TUNE_FULL_SA, 1)
+L.svfm_set_tuning(_ffi.SVFM_TUNE_SWEEP_OCC, 1)
 print("sanitize_case: all results match the oracle")

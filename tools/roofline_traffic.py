@@ -37,7 +37,7 @@ def phase_of(name: str) -> str:
         return "search"
     if re.search(r"sb_scan_kernel|DeviceScan", name):
         return "scan"
-    if re.search(r"locate_warp_kernel|locate_rows_kernel", name):
+    if re.search(r"locate_warp_kernel|locate_rows_kernel|locate_direct_kernel", name):
         return "locate"
     if re.search(r"sb_place_kernel|scatter_counts_kernel|run_starts_kernel|narrow_offs_kernel|add_base_kernel", name):
         return "sortback"
