@@ -338,7 +338,11 @@ static int run_build_ext(svfm_index* ix, uint64_t ext_bits) {
     const uint64_t s_eff = ix->symbols_present;
     uint64_t budget = 1ull << (ext_bits > 32 ? 32 : ext_bits);
     if (ext_bits == 0 || s_eff < 2 || s_eff > 64) return SVFM_OK;
-    const uint64_t by_text = ix->text_len / 2 > s_eff ? ix->text_len / 2 : s_eff;
+    // at most two entries per text symbol (an interval of 0.5 rows on average: most lookups of patterns that occur end on a
+    // single row, and longer keys would only add empty entries); SVFM_EXT_PER_TEXT overrides the factor
+    static const double per_text = [] { const char* e = std::getenv("SVFM_EXT_PER_TEXT"); return e ? atof(e) : 2.0; }();
+    const uint64_t cap_text = (uint64_t)((double)ix->text_len * per_text);
+    const uint64_t by_text = cap_text > s_eff ? cap_text : s_eff;
     if (budget > by_text) budget = by_text;
     uint32_t m = 1;
     uint64_t entries = s_eff;

@@ -229,22 +229,30 @@ static std::atomic<uint64_t> g_sweep_min{[] {
 static uint64_t sweep_min_patterns(const svfm_index* ix, bool for_locate = true) {
     const uint64_t v = g_sweep_min.load();
     if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
-    if (ix->d_text && ix->d_fsa) return for_locate ? (uint64_t)(24u << 20) : (uint64_t)(8u << 20);
+    if (ix->d_text && ix->d_fsa) {
+        // (2^28-entry table: break-even ~24 M / ~8 M; with the default 2^30-entry table the plain kernel runs 10^8 patterns in
+        // 11.6 ms against 10.6 ms, 8.3 M in 1.06 ms against 1.6 ms)
+        const bool big = ix->ext_entries > (1ull << 28);
+        return for_locate ? (uint64_t)((big ? 48u : 24u) << 20) : (uint64_t)((big ? 16u : 8u) << 20);
+    }
     return ix->ext_entries >= (1ull << 26) ? (uint64_t)(10u << 20) : (uint64_t)(5u << 20);
 }
 static std::atomic<uint64_t> g_ext_bits{[] {  // extended table: at most 2^bits entries (0 = no table)
     const char* e = std::getenv("SVFM_EXT_BITS");
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
-// AUTO: 2^28 entries (2 GiB with u32 positions: 14 DNA symbols per lookup) when that is at most 1/16 of the device
-// memory still free after the blob upload -- HBM capacity is what a B200 has plenty of -- else 2^24 (128 MiB).
+// AUTO: HBM capacity is what a B200 has plenty of -- 2^30 entries (8 GiB with u32 positions: 15 DNA symbols per lookup on
+// a >= 0.54 Gbp text) when that is at most 1/8 of the device memory still free after the blob upload, else 2^28 (2 GiB, 14
+// symbols) when that is at most 1/16, else 2^24 (128 MiB).  Measured on B200, 1 Gbp DNA, 10^8 20-mers, count+locate: 2^28 ->
+// 2^30 entries takes the sweep search from 11.05 to 10.63 ms and the plain kernel from 14.1 to 11.6 ms.
 static uint64_t ext_bits_for(const svfm_index* ix) {
     const uint64_t v = g_ext_bits.load();
     if (v != (uint64_t)SVFM_TUNE_AUTO) return v;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return 24; }
-    const uint64_t big = (1ull << 28) * 2 * (ix->type.pos_bits / 8);
-    return big <= free_b / 16 ? 28 : 24;
+    const uint64_t pair = 2 * (uint64_t)(ix->type.pos_bits / 8);
+    if ((pair << 30) <= free_b / 8) return 30;
+    return (pair << 28) <= free_b / 16 ? 28 : 24;
 }
 static std::atomic<uint64_t> g_ilv{[] {  // build the interleaved occ copy at load
     const char* e = std::getenv("SVFM_ILV");
