@@ -189,17 +189,18 @@ void svfm_host_free(void* p);
  *                      UINT64_MAX = never; default SVFM_TUNE_AUTO = never when the index has an extended k-mer table
  *                      -- nothing is left to share after the lookup -- else 131072; env SVFM_SORT_MIN).
  * SVFM_TUNE_CHUNK    : the host-buffer entry points cut a batch into chunks of about this many patterns and
- *                      pipeline upload / kernels / download (0 = one chunk; default SVFM_TUNE_AUTO = 8 Mi; env SVFM_CHUNK).
+ *                      pipeline upload / kernels / download (0 = one chunk; default SVFM_TUNE_AUTO = 4 Mi; env SVFM_CHUNK).
  * SVFM_TUNE_SWEEP_MIN: fixed-length batches with at least this many patterns use the sweep search -- the batch is
  *                      kept sorted by SA position and moves through the index as streams (default SVFM_TUNE_AUTO = the
- *                      measured break-even with the plain search kernel on a 1 Gbp index: 24 Mi patterns for locate and
- *                      8 Mi for count when the index has its packed text copy and expanded suffix array, else 5 Mi
- *                      with a 2^24-entry extended table and 10 Mi with a 2^28-entry one; env SVFM_SWEEP_MIN).
+ *                      measured break-even with the plain search kernel on a 1 Gbp index: 48 Mi patterns for locate and
+ *                      16 Mi for count when the index has its packed text copy, expanded suffix array and a 2^30-entry
+ *                      extended table (24 Mi / 8 Mi with a 2^28-entry one), else 5 Mi with a 2^24-entry extended table
+ *                      and 10 Mi with a 2^28-entry one; env SVFM_SWEEP_MIN).
  * SVFM_TUNE_EXT_BITS : indexes loaded from now on get an extended k-mer table of at most 2^value entries (and at most
- *                      text_len / 2), derived from the blob at load (0 = none; default SVFM_TUNE_AUTO = 28, i.e. 2 GiB
- *                      for u32 positions, when that is under 1/16 of the free device memory, else 24 = 128 MiB; env
- *                      SVFM_EXT_BITS).
- * SVFM_TUNE_WORKERS  : host threads / streams per host-buffer call (default 3; env SVFM_WORKERS).
+ *                      two per text symbol), derived from the blob at load (0 = none; default SVFM_TUNE_AUTO = 30, i.e.
+ *                      8 GiB for u32 positions, when that is under 1/8 of the free device memory, else 28 = 2 GiB when
+ *                      under 1/16, else 24 = 128 MiB; env SVFM_EXT_BITS).
+ * SVFM_TUNE_WORKERS  : host threads / compute streams per host-buffer call (default 2; env SVFM_WORKERS).
  * SVFM_TUNE_ILV      : indexes loaded from now on also get an interleaved copy of the occ data -- block q and checkpoint
  *                      row q in one aligned 32/64/128-byte slot -- which the gather-bound kernels read instead of the two
  *                      blob sections (1 = build, the default; 0 = search the blob in place only; env SVFM_ILV).

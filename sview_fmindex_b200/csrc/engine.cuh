@@ -64,6 +64,12 @@ struct svfm_uploader {
 struct svfm_session {
     svfm_index* ix = nullptr;
     cudaStream_t stream = nullptr;
+    // host-buffer locate calls: the results of a chunk leave on copy_stream while `stream` already runs the search of the
+    // worker's next chunk; ev_done = the chunk's kernels are finished, ev_copied = its downloads are (the next chunk waits
+    // for it right before its first kernel that writes out_offs / positions)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;
     svfm::DeviceBuffer pats, offs, unpacked, sp, cnt, counts_out, woffs, out_offs, offs64, positions, positions_alt, cub_temp;
     svfm::DeviceBuffer keys0, keys1, vals0, vals1;          // locality sort (u64 packed pattern, u32 pattern index)
     svfm::DeviceBuffer pay0, pay1, items0, items1, sweep_hist, sweep_desc;  // sweep search: items moving through the partitions

@@ -140,6 +140,9 @@ static int session_new(svfm_index* ix, svfm_session** out) {
     svfm_session* s = new svfm_session();
     s->ix = ix;
     cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(uint64_t), cudaHostAllocDefault);
@@ -168,6 +171,9 @@ static void session_delete(svfm_session* s) {
     if (!s) return;
     cudaSetDevice(s->ix->device);
     if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
+    if (s->ev_copied) cudaEventDestroy(s->ev_copied);
     if (s->d_err) cudaFree(s->d_err);
     if (s->d_counters) cudaFree(s->d_counters);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -718,6 +724,17 @@ static int count_device(svfm_session* s, const PatternBatch& pb, void* d_counts_
 //   SVFM_SORTED on a large batch, or 2^32 and more occurrences: scan (work order) -> LF-walk into records -> radix sort
 //                 by position -> stable radix sort by pattern index -> CSR offsets
 // d_out_offs: u64[n+1], or u32[n+1] with SVFM_OFFS32 (SVFM_ERR_TOO_LARGE when the total does not fit).
+// The downloads of the session's previous chunk (locate_host) read out_offs / positions: every kernel that writes them
+// is ordered behind the copies.  Called right before the first such kernel, i.e. AFTER the search kernels are enqueued,
+// so that the search of this chunk overlaps the downloads of the last one.
+static int order_behind_pending_copy(svfm_session* s, bool host_wait = false) {
+    if (!s->copy_pending) return SVFM_OK;
+    if (host_wait) SVFM_CUDA(cudaEventSynchronize(s->ev_copied));
+    else SVFM_CUDA(cudaStreamWaitEvent(s->stream, s->ev_copied, 0));
+    s->copy_pending = false;
+    return SVFM_OK;
+}
+
 static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags, void* d_out_offs,
                          void** d_positions, uint64_t* total_out) {
     const uint64_t P = s->ix->type.pos_bits / 8;
@@ -780,6 +797,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         *total_out = total;
         if (total < 0xffffffffull) {  // the 32-bit bucket counters did not wrap
             const uint64_t rec_bytes = P == 4 ? 8 : 16;
+            if ((std::max(total, s->reserve_n) + 1) * P > s->positions.cap && (rc = order_behind_pending_copy(s, true))) return rc;  // the buffer is about to move
             if ((rc = s->positions.reserve((std::max(total, s->reserve_n) + 1) * P)) ||
                 (rc = s->sb_recs.reserve((std::max(total, s->reserve_n) + 1) * rec_bytes)))
                 return rc;
@@ -787,6 +805,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
             if ((rc = dispatch_locate(s, pb.n, idx, s->sp.ptr, s->cnt.ptr, nullptr, total, heavy_seen, nullptr, nullptr, s->sb_recs.ptr,
                                       (unsigned long long*)s->sb_cursor.ptr, d_resolved)))
                 return rc;
+            if ((rc = order_behind_pending_copy(s))) return rc;
             return SVFM_BY_POS(run_sb_place, s, pb.n, nb, d_out_offs, offs32, s->positions.ptr);
         }
         bucket = false;  // 2^32 records and more: radix sort-back
@@ -801,6 +820,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
         if ((rc = s->woffs.reserve((rn + 1) * 8))) return rc;
         offs_work = (uint64_t*)s->woffs.ptr;
     }
+    if ((rc = order_behind_pending_copy(s))) return rc;   // the scan may write out_offs itself
     if ((rc = dispatch_scan(s, pb.n, s->cnt.ptr, offs_work))) return rc;
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[0], offs_work + pb.n, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     SVFM_CUDA(cudaMemcpyAsync(&s->h_pinned[1], s->d_err, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -811,7 +831,7 @@ static int locate_device(svfm_session* s, const PatternBatch& pb, uint32_t flags
     const uint64_t heavy_seen = s->h_pinned[3];
     *total_out = total;
     if (offs32 && total > 0xffffffffull) return SVFM_ERR_TOO_LARGE;
-    if ((rc = s->positions.reserve((std::max(total, s->reserve_n) + 1) * P))) return rc;
+    if ((rc = s->positions.reserve((std::max(total, s->reserve_n) + 1) * P))) return rc;   // (no copy is pending any more)
     const bool records = reordered || by_position;
     if (records && (rc = s->rec_key.reserve((total + 1) * 4))) return rc;
     *d_positions = s->positions.ptr;
@@ -855,8 +875,11 @@ static std::atomic<uint64_t> g_chunk_patterns{[] {
     return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)SVFM_TUNE_AUTO;
 }()};
 static std::atomic<uint64_t> g_host_workers{[] {
+    // 2: each worker overlaps the downloads of its last chunk with the search of its next one (copy stream), so two of them
+    // keep the copy engines and the SMs busy; a third only adds contention between kernels (measured 4.77 / 4.98 / 4.60 G
+    // patterns/s end to end with 3 / 2 / 4 workers, 10^8 packed 20-mers)
     const char* e = std::getenv("SVFM_WORKERS");
-    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)3;
+    return e ? (uint64_t)std::strtoull(e, nullptr, 10) : (uint64_t)2;
 }()};
 static const bool g_trace = std::getenv("SVFM_TRACE") != nullptr;
 static double now_ms() {
@@ -909,16 +932,16 @@ struct ChunkPlan {
 // aligned for the TMA staging).  The LAST chunk is halved repeatedly (down to ~1 Mi patterns): the upload stream is the
 // bottleneck of a host batch, so what remains after the last byte has arrived -- kernels + download of the final
 // chunk -- should be small.
-// AUTO: 8 Mi patterns.  Measured on B200, 10^8 20-mers, count+locate, pinned buffers (end-to-end G patterns/s): byte patterns
-// 2.45 / 2.41 / 2.36 / 2.17 with 4 / 8 / 12 / 32 Mi chunks (the upload bounds the call: 2 GB at PCIe speed); 2-bit packed
-// patterns 4.39 / 4.46 / 4.33 / 3.89 / 3.65 / 3.31 with 4 / 6 / 8 / 12 / 16 / 32 Mi chunks -- chunks this size take the plain
-// search kernel (see sweep_min_patterns), whose time per pattern does not depend on the batch size, and small chunks keep
-// the head (first upload + first kernels) and the tail (last download) of the pipeline short.
+// AUTO: 4 Mi patterns.  Measured on B200, 10^8 20-mers, count+locate, pinned buffers (end-to-end G patterns/s, 2 workers, results
+// leaving on the sessions' copy streams): 2-bit packed patterns 4.66 / 5.12 / 5.07 / 4.98 with 2 / 4 / 6 / 8 Mi chunks; byte
+// patterns 2.35-2.41 whatever the chunk size (the upload bounds that call: 2 GB at PCIe speed).  Chunks this size take the
+// plain search kernel (see sweep_min_patterns), whose time per pattern hardly depends on the batch size, and small chunks
+// keep the head (first upload + first kernels) and the tail (last download) of the pipeline short.
 static ChunkPlan plan_chunks(uint64_t n, uint64_t bytes_per_pattern = 0) {
     ChunkPlan p;
     p.n = n;
     uint64_t c = g_chunk_patterns.load();
-    if (c == (uint64_t)SVFM_TUNE_AUTO) c = 8u << 20;
+    if (c == (uint64_t)SVFM_TUNE_AUTO) c = 4u << 20;
     (void)bytes_per_pattern;
     if (c == 0) c = n;
     uint64_t k = (n + c - 1) / c;
@@ -1102,7 +1125,12 @@ static int run_workers(svfm_index* ix, uint64_t c0, uint64_t c1, uint64_t reserv
             }
             if (!run || rc != SVFM_OK) per_chunk(nullptr, c);  // publish "nothing": nobody may wait on this chunk forever
         }
-        if (lease.s) { cudaStreamSynchronize(lease.s->stream); lease.s->reserve_n = 0; }
+        if (lease.s) {
+            cudaStreamSynchronize(lease.s->stream);
+            cudaStreamSynchronize(lease.s->copy_stream);   // deferred downloads of the last chunk (locate_host)
+            lease.s->copy_pending = false;
+            lease.s->reserve_n = 0;
+        }
     };
     if (workers <= 1) {
         prologue();
@@ -1401,20 +1429,25 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
             g_launches++;
             SVFM_CUDA(cudaGetLastError());
         }
-        SVFM_CUDA(cudaMemcpyAsync((uint8_t*)out_offs + a * OW, s->out_offs.ptr, n_offs * OW, cudaMemcpyDeviceToHost, s->stream));
+        // downloads on the session's copy stream, behind this chunk's kernels; the worker goes on to its next chunk
+        SVFM_CUDA(cudaEventRecord(s->ev_done, s->stream));
+        SVFM_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_done, 0));
+        SVFM_CUDA(cudaMemcpyAsync((uint8_t*)out_offs + a * OW, s->out_offs.ptr, n_offs * OW, cudaMemcpyDeviceToHost, s->copy_stream));
         if (total) {
             if (alloc_out) {
                 void* buf = result_alloc(total * P);
-                if (!buf) { cudaStreamSynchronize(s->stream); g_last_error = "result allocation failed"; return SVFM_ERR_NOMEM; }
+                if (!buf) { cudaStreamSynchronize(s->copy_stream); g_last_error = "result allocation failed"; return SVFM_ERR_NOMEM; }
                 chunk_bufs[c] = buf;
-                SVFM_CUDA(cudaMemcpyAsync(buf, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
+                SVFM_CUDA(cudaMemcpyAsync(buf, d_positions, total * P, cudaMemcpyDeviceToHost, s->copy_stream));
             } else if (base + total <= capacity) {
-                SVFM_CUDA(cudaMemcpyAsync((uint8_t*)positions + base * P, d_positions, total * P, cudaMemcpyDeviceToHost, s->stream));
+                SVFM_CUDA(cudaMemcpyAsync((uint8_t*)positions + base * P, d_positions, total * P, cudaMemcpyDeviceToHost, s->copy_stream));
             } else {
                 overflow.store(true);
             }
         }
-        SVFM_CUDA(cudaStreamSynchronize(s->stream));
+        SVFM_CUDA(cudaEventRecord(s->ev_copied, s->copy_stream));
+        s->copy_pending = true;
+        if (g_trace) SVFM_CUDA(cudaStreamSynchronize(s->copy_stream));
         if (g_trace)
             std::fprintf(stderr, "[svfm trace] chunk %llu n=%llu: start %.2f  h2d %.2f  kernels %.2f  d2h %.2f ms\n",
                          (unsigned long long)c, (unsigned long long)m, t_0 - t_begin, t_1 - t_0, t_2 - t_1, now_ms() - t_2);
