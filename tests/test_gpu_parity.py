@@ -414,8 +414,9 @@ def test_randomized_configs(oracle, fm):
         ora, gpu, table, sc = _pair(oracle, fm, bytes(text), symbols, p, nn, v, k, r, passthrough=passthrough,
                                     with_wildcard=with_wildcard)
         src = table[text] if passthrough else text
-        # fixed-length batch
-        ln = int(rng.integers(1, min(n, 24) + 1))
+        # fixed-length batch: short patterns (sweep-eligible when forced on) and, every other case, lengths up to 200
+        # (beyond what a sweep item holds: plain kernel, with and without text verification / the expanded suffix array)
+        ln = int(rng.integers(1, min(n, 24 if case % 2 == 0 else 200) + 1))
         m = 257
         starts = rng.integers(0, n - ln + 1, size=m)
         pats = src[starts[:, None] + np.arange(ln)[None, :]].copy()
