@@ -16,6 +16,10 @@ struct PatternBatch {
     uint32_t fixed_len;
     uint32_t reversed;     // patterns stored back-to-front (rev-iter twins, locate/with_rev_iter.rs)
     uint32_t preencoded;   // bytes are symbol indices already (packed entry points): the encoding table is skipped
+    // packed_bits > 0: `pats` still holds the caller's PACKED patterns (packed_bpp bytes each, see unpack_patterns_kernel) and
+    // fixed_len is the number of symbols; search_kernel unpacks them while staging a CTA's patterns in shared memory, so the
+    // one-byte-per-symbol copy never exists in HBM.  Only the plain kernel reads this form (svfm_api.cu decides).
+    uint32_t packed_bits = 0, packed_bpp = 0;
 };
 
 // Packed fixed-length patterns (svfm_*_batch_packed): symbol indices, `bits` bits each, first symbol in the lowest bits
@@ -501,6 +505,32 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io,
             skew = (uint32_t)(reinterpret_cast<uintptr_t>(pb.pats + b0) & 3u);   // keep the word alignment of the source
             staged = b1 >= b0 && b1 - b0 + skew <= (uint64_t)stage_bytes;
         }
+        if (pb.packed_bits) {   // fixed-length packed patterns: the stage holds them unpacked (host: the CTA's patterns always fit)
+            b0 = wb * (uint64_t)pb.fixed_len;
+            b1 = we * (uint64_t)pb.fixed_len;
+            skew = 0;
+            staged = true;
+            SVFM_ASSERT(may_stage && b1 - b0 <= (uint64_t)stage_bytes);
+            __syncthreads();
+            const uint32_t nbytes = (uint32_t)(b1 - b0), len = pb.fixed_len, bits_p = pb.packed_bits, mask = (1u << bits_p) - 1u;
+            const uint8_t* src = pb.pats + wb * (uint64_t)pb.packed_bpp;
+            for (uint32_t o = threadIdx.x * 4u; o < nbytes; o += blockDim.x * 4u) {
+                uint32_t i = o / len, j = o - i * len, word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    if (o + b < nbytes) {
+                        const uint32_t bit = j * bits_p;
+                        const uint8_t* q = src + (uint64_t)i * pb.packed_bpp + (bit >> 3);
+                        uint32_t v = __ldg(q);
+                        if ((bit & 7u) + bits_p > 8u) v |= (uint32_t)__ldg(q + 1) << 8;   // bits <= 8: a symbol spans at most two bytes
+                        word |= ((v >> (bit & 7u)) & mask) << (8 * b);
+                        if (++j == len) { j = 0; i++; }
+                    }
+                }
+                *reinterpret_cast<uint32_t*>(s_stage + o) = word;   // the stage is 16-byte aligned and padded to a multiple of 4
+            }
+            __syncthreads();
+        } else {
         if (may_stage) __syncthreads();   // the previous range is no longer read
         if (staged) {
             const uint8_t* src = pb.pats + b0;
@@ -515,6 +545,7 @@ search_kernel(const DevIndex<P> ix, const PatternBatch pb, const SearchIO<P> io,
             if (threadIdx.x < nbytes - tail0) s_stage[skew + tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
         }
         if (may_stage) __syncthreads();
+        }
         if (w >= pb.n) continue;
         const uint64_t i = io.idx ? (uint64_t)io.idx[w] : w;
         const uint64_t key = io.keys ? io.keys[w] : 0ull;

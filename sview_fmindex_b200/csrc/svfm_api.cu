@@ -1227,8 +1227,21 @@ struct PackedSpec {
     uint32_t bits = 0;  // 0: not packed
     uint32_t len = 0;   // symbols per pattern
 };
-static int unpack_chunk(svfm_session* s, const PackedSpec& spec, PatternBatch& pb) {
+// Packed host patterns of one chunk.  When the chunk is going to take the plain search kernel anyway (no sweep search, no
+// locality sort) and a CTA's patterns fit its stage, the kernel unpacks them itself while staging (PatternBatch::packed_bits)
+// and nothing is expanded in HBM; otherwise unpack_patterns_kernel writes the one-byte-per-symbol form first.
+static const bool g_packed_direct = [] { const char* e = std::getenv("SVFM_PACKED_DIRECT"); return e ? atoi(e) != 0 : true; }();
+static int unpack_chunk(svfm_session* s, const PackedSpec& spec, PatternBatch& pb, bool for_locate) {
     if (!spec.bits) return SVFM_OK;
+    const svfm_index* ix = s->ix;
+    if (g_packed_direct && ix->ext_m != 0 && pb.n < sweep_min_patterns(ix, for_locate) && pb.n < sort_min_patterns(ix) &&
+        (uint64_t)SEARCH_THREADS * spec.len + 4 <= (uint64_t)SEARCH_STAGE_MAX) {
+        pb.packed_bits = spec.bits;
+        pb.packed_bpp = pb.fixed_len;
+        pb.fixed_len = spec.len;
+        pb.preencoded = 1;
+        return SVFM_OK;
+    }
     const uint64_t bytes = pb.n * (uint64_t)spec.len;
     int rc;
     if ((rc = s->unpacked.reserve(rsv(s, pb.n) * (uint64_t)spec.len + 256))) return rc;
@@ -1259,7 +1272,7 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
         }
         PatternBatch pb;
         if ((r = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return r;
-        if ((r = unpack_chunk(s, spec, pb))) return r;
+        if ((r = unpack_chunk(s, spec, pb, false))) return r;
         if ((r = s->counts_out.reserve(n * P))) return r;
         if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
         SVFM_CUDA(cudaMemcpyAsync(counts_out, s->counts_out.ptr, n * P, cudaMemcpyDeviceToHost, s->stream));
@@ -1279,7 +1292,7 @@ static int count_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs,
             PatternBatch pb;
             int r;
             if ((r = await_chunk(s, cp, g, c, pb))) return r;
-            if ((r = unpack_chunk(s, spec, pb))) return r;
+            if ((r = unpack_chunk(s, spec, pb, false))) return r;
             if ((r = s->counts_out.reserve(rsv(s, b - a) * P))) return r;  // not s->cnt: count_device uses that in work order
             if ((r = count_device(s, pb, s->counts_out.ptr))) return r;
             SVFM_CUDA(cudaMemcpyAsync((uint8_t*)counts_out + a * P, s->counts_out.ptr, (b - a) * P, cudaMemcpyDeviceToHost, s->stream));
@@ -1357,7 +1370,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         }
         PatternBatch pb;
         if ((rc = upload_direct(s, pats, offs, n, fixed_len, flags, pb))) return rc;
-        if ((rc = unpack_chunk(s, spec, pb))) return rc;
+        if ((rc = unpack_chunk(s, spec, pb, true))) return rc;
         if ((rc = s->out_offs.reserve((n + 1) * sizeof(uint64_t)))) return rc;
         void* d_positions = nullptr;
         uint64_t total = 0;
@@ -1406,7 +1419,7 @@ static int locate_host(svfm_index* ix, const uint8_t* pats, const uint64_t* offs
         if ((r = await_chunk(s, cp, g, c, pb))) return r;
         if (g_trace) { cudaStreamSynchronize(s->stream); }
         const double t_1 = g_trace ? now_ms() : 0;
-        if ((r = unpack_chunk(s, spec, pb))) return r;
+        if ((r = unpack_chunk(s, spec, pb, true))) return r;
         if ((r = s->out_offs.reserve((rsv(s, m) + 1) * sizeof(uint64_t)))) return r;
         void* d_positions = nullptr;
         uint64_t total = 0;
