@@ -429,7 +429,7 @@ int run_sweep_presort(svfm_session* s, const PatternBatch& pb, const SortPlan& p
     const uint32_t len = pb.fixed_len, bits = plan.bits;
     const uint32_t digit_bits = bits * plan.steps_per_round, nb_max = 1u << digit_bits;
     // Only the top 16 bits of the table index are sorted (two radix passes).  Items that differ in the lower bits only sit
-    // within 1/65536 of the SA (a 2^28-entry DNA table on 1 Gbp: 4096 entries, ~240 occ blocks = 10 KB of index data, which
+    // within 1/65536 of the SA (a DNA table on 1 Gbp: 4096-16384 entries, ~240 occ blocks = 10 KB of index data, which
     // the CTAs working on that stretch share through L1/L2), and correctness never depends on the order.  Measured on B200,
     // 10^8 20-mers: 28 bits (4 passes) and 24 bits (3 passes) give the same round times; 16 bits make the first round
     // 0.6 ms slower and the sort 0.85 ms shorter (14.65 against 14.87 ms per batch); SVFM_PRESORT_BITS overrides.
@@ -610,8 +610,8 @@ static int build_ext_table(svfm_index* ix) {
     if (!ops) return SVFM_ERR_BAD_TYPE;
     int rc = ops->build_ext(ix->type.planes, ix, ext_bits_for(ix));
     if (rc) return rc;
-    // north_star: "the k-mer table is staged in shared memory or an L2-persisting window".  The default table (2^28 entries,
-    // 2 GiB) is far larger than L2 and is read once per pattern, so nothing is pinned for it; a table of at most 64 MiB
+    // north_star: "the k-mer table is staged in shared memory or an L2-persisting window".  The default table (2^30 entries,
+    // 8 GiB) is far larger than L2 and is read once per pattern, so nothing is pinned for it; a table of at most 64 MiB
     // (SVFM_TUNE_EXT_BITS <= 23 for 32-bit positions: memory-constrained deployments) is marked persisting in L2 for every
     // kernel of every session of this index (cudaAccessPolicyWindow, set per stream in session_new).
     const uint64_t bytes = ix->d_ext ? ix->ext_entries * 2 * (ix->type.pos_bits / 8) : 0;
